@@ -115,6 +115,8 @@ def lib() -> C.CDLL:
         for f in (L.orc_dist_anchor, L.orc_dist_anchor_spec):
             f.restype = Model
             f.argtypes = [C.POINTER(OrcEsa), C.c_char_p, C.c_size_t, C.c_size_t, C.c_int]
+        L.orc_sweep_check.restype = C.c_size_t
+        L.orc_sweep_check.argtypes = [C.POINTER(OrcEsa), C.c_int]
         L.orc_model_average.restype = Model
         L.orc_model_average.argtypes = [C.POINTER(Model), C.POINTER(Model)]
         L.orc_model_coverage.restype = C.c_double

@@ -706,3 +706,26 @@ int orc_rows(const char *const *seqs, const size_t *lens, size_t n, size_t s_beg
 	}
 	return 0;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* test/test_esa.c:38-44,172-203 ("/esa/full cache"): for ALL ACGT strings of length depth,
+ * the cached search, the uncached child-table search and the spec must agree on (l, i, j),
+ * the match must spell the query prefix and must be maximal. Returns the number of
+ * strings that violate any of these (0 = pass). */
+size_t orc_sweep_check(const orc_esa *E, int depth) {
+	size_t bad = 0, total = (size_t)1 << (2 * depth);
+	char q[40];
+	if (depth >= (int)sizeof q) return (size_t)-1;
+	q[depth] = '\0';
+	for (size_t s = 0; s < total; s++) {
+		for (int d = 0; d < depth; d++) q[d] = "ACGT"[(s >> (2 * (depth - 1 - d))) & 3];
+		orc_interval a = orc_get_match_cached(E, q, (size_t)depth);
+		orc_interval b = orc_get_match_cld(E, q, (size_t)depth);
+		orc_interval c = orc_get_match(E, q, (size_t)depth);
+		int ok = a.l == b.l && a.i == b.i && a.j == b.j && a.l == c.l && a.i == c.i && a.j == c.j;
+		ok = ok && strncmp(q, E->S + E->SA[a.i], (size_t)a.l) == 0;
+		ok = ok && (q[a.l] != E->S[a.l + E->SA[a.i]] || q[a.l] == '\0');
+		bad += !ok;
+	}
+	return bad;
+}

@@ -75,9 +75,15 @@ orc_interval orc_get_match(const orc_esa *E, const char *query, size_t qlen);
 orc_interval orc_get_match_cld(const orc_esa *E, const char *query, size_t qlen);
 orc_interval orc_get_match_cached(const orc_esa *E, const char *query, size_t qlen);
 
+/* test/test_esa.c:172-203 restated: exhaustive agreement sweep over all 4^depth queries */
+size_t orc_sweep_check(const orc_esa *E, int depth);
+
 /* src/process.c:141-214 */
 orc_model orc_dist_anchor(const orc_esa *E, const char *query, size_t qlen, size_t threshold,
 						  int model_id);
+/* same walk with the ESA lookup replaced by the spec search orc_get_match */
+orc_model orc_dist_anchor_spec(const orc_esa *E, const char *query, size_t qlen,
+							   size_t threshold, int model_id);
 
 /* src/model.c:246-279, 309-337 */
 void orc_model_count_equal(orc_model *M, const char *q, size_t len, int model_id);
