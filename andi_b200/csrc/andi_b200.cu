@@ -1,0 +1,942 @@
+// andi_b200/csrc/andi_b200.cu -- C ABI of libandi_b200.so (include/andi_b200.h), host side.
+//
+// Orchestrates the sm_100a kernels of esa_kernels.cuh / walk_kernels.cuh. One context per
+// GPU, one stream, stream-ordered allocations (cudaMallocAsync) so index construction for
+// thousands of subjects never calls cudaMalloc in the steady state. Radix sort / scan / select
+// are CUB device primitives (library code, like cuBLAS for a GEMM); every other kernel is ours.
+#include "../../include/andi_b200.h"
+#include "walk_kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------ plumbing
+
+struct andi_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	std::string err;
+	int sm_count = 148;
+
+	// pool (src/process.h:11 `seq_t *sequences, size_t n`)
+	size_t n = 0;
+	std::vector<size_t> len;
+	std::vector<double> gc;
+	std::vector<int> has_sep;
+	std::vector<size_t> word_off;  // u64-word offset of each sequence's planes
+	u64 *pool_code = nullptr, *pool_spec = nullptr;
+	QueryView *d_queries = nullptr;
+	bool any_sep = false;
+
+	andi_stats st{};
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> esa_ev, walk_ev;
+	std::vector<cudaEvent_t> free_ev;
+	cudaEvent_t first_ev = nullptr, last_ev = nullptr;
+};
+
+struct andi_esa {
+	andi_ctx *ctx = nullptr;
+	u32 n = 0, N = 0;
+	u64 *code = nullptr, *spec = nullptr;
+	u32 *SA = nullptr;
+	int32_t *LCP = nullptr;
+	u32 *dir = nullptr;
+	PresenceLevels present{};
+	int K = 0;
+	bool has_sep = false;
+	bool full = false;
+	int32_t *CLD = nullptr;
+	char *FVC = nullptr;
+	Inter *cache = nullptr;
+	u32 self = 0xffffffffu;
+	u32 threshold = 0;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess) {                                                                   \
+			ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+			return ANDI_ERR_CUDA;                                                                  \
+		}                                                                                          \
+	} while (0)
+
+static inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+static inline size_t plane_words(size_t chars) { return chars / 32 + 3; }  // >= 2 guard words
+
+template <class T>
+static cudaError_t dalloc(andi_ctx *ctx, T **p, size_t count) {
+	return cudaMallocAsync((void **)p, std::max<size_t>(count, 1) * sizeof(T), ctx->stream);
+}
+template <class T>
+static void dfree(andi_ctx *ctx, T *&p) {
+	if (p) cudaFreeAsync((void *)p, ctx->stream);
+	p = nullptr;
+}
+
+static cudaEvent_t get_event(andi_ctx *ctx) {
+	if (!ctx->free_ev.empty()) {
+		cudaEvent_t e = ctx->free_ev.back();
+		ctx->free_ev.pop_back();
+		return e;
+	}
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+
+static void mark(andi_ctx *ctx, cudaEvent_t e) {
+	cudaEventRecord(e, ctx->stream);
+}
+
+// Fold finished event pairs into the stats (call after a stream synchronize).
+static void harvest_events(andi_ctx *ctx) {
+	float ms;
+	for (auto &p : ctx->esa_ev) {
+		if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) ctx->st.esa_ms += ms;
+		ctx->free_ev.push_back(p.first), ctx->free_ev.push_back(p.second);
+	}
+	for (auto &p : ctx->walk_ev) {
+		if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) ctx->st.walk_ms += ms;
+		ctx->free_ev.push_back(p.first), ctx->free_ev.push_back(p.second);
+	}
+	ctx->esa_ev.clear(), ctx->walk_ev.clear();
+	if (ctx->first_ev && ctx->last_ev) {
+		if (cudaEventElapsedTime(&ms, ctx->first_ev, ctx->last_ev) == cudaSuccess) ctx->st.total_ms += ms;
+		ctx->free_ev.push_back(ctx->first_ev), ctx->free_ev.push_back(ctx->last_ev);
+		ctx->first_ev = ctx->last_ev = nullptr;
+	}
+}
+
+extern "C" int andi_ctx_create(int device, void *stream, andi_ctx **out) {
+	if (!out) return ANDI_ERR_ARG;
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || device < 0 || device >= count) {
+		g_create_err = e != cudaSuccess ? std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)
+										: "no such CUDA device";
+		return ANDI_ERR_CUDA;
+	}
+	andi_ctx *ctx = new andi_ctx();
+	ctx->device = device;
+	if ((e = cudaSetDevice(device)) != cudaSuccess) {
+		g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+		delete ctx;
+		return ANDI_ERR_CUDA;
+	}
+	if (stream) {
+		ctx->stream = (cudaStream_t)stream;
+	} else {
+		if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+			g_create_err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+			delete ctx;
+			return ANDI_ERR_CUDA;
+		}
+		ctx->own_stream = true;
+	}
+	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+	// keep freed blocks in the stream-ordered pool instead of returning them to the driver
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+		uint64_t keep = UINT64_MAX;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
+	*out = ctx;
+	return ANDI_OK;
+}
+
+static void pool_release(andi_ctx *ctx) {
+	dfree(ctx, ctx->pool_code);
+	dfree(ctx, ctx->pool_spec);
+	dfree(ctx, ctx->d_queries);
+	ctx->n = 0;
+	ctx->len.clear(), ctx->gc.clear(), ctx->has_sep.clear(), ctx->word_off.clear();
+	ctx->any_sep = false;
+}
+
+extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	harvest_events(ctx);
+	pool_release(ctx);
+	cudaStreamSynchronize(ctx->stream);
+	for (auto e : ctx->free_ev) cudaEventDestroy(e);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" const char *andi_last_error(const andi_ctx *ctx) {
+	return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int andi_get_stats(const andi_ctx *ctx, andi_stats *out) {
+	if (!ctx || !out) return ANDI_ERR_ARG;
+	*out = ctx->st;
+	return ANDI_OK;
+}
+
+extern "C" void andi_reset_stats(andi_ctx *ctx) {
+	if (ctx) ctx->st = andi_stats{};
+}
+
+// ------------------------------------------------------------------ threshold (host, FP64)
+// src/sequence.c:296-373. Kept on the host in double precision with the reference's
+// evaluation order so that the integer threshold is identical.
+
+static size_t n_choose_k(size_t n, size_t k) {
+	if (n == 0 || k > n) return 0;
+	if (k == 0 || k == n) return 1;
+	k = std::min(k, n - k);
+	size_t r = 1;
+	for (size_t i = 1; i <= k; i++) r = r * (n - k + i) / i;
+	return r;
+}
+
+static double shustring_cdf(size_t x, double p, size_t l) {
+	const double xx = (double)x, ll = (double)l;
+	double acc = 0.0;
+	for (size_t k = 0; k <= x; k++) {
+		double kk = (double)k;
+		double t = pow(p, kk) * pow(0.5 - p, xx - kk);
+		acc += pow(2, xx) * (t * pow(1 - t, ll)) * (double)n_choose_k(x, k);
+		if (acc >= 1.0) return 1.0;
+	}
+	return acc;
+}
+
+extern "C" size_t andi_threshold(double p_value, double gc, size_t rs_len) {
+	size_t x = 1;
+	while (shustring_cdf(x, gc / 2, rs_len) < 1 - p_value) x++;
+	return x;
+}
+
+// ------------------------------------------------------------------ pool
+
+static int pool_finish(andi_ctx *ctx, const unsigned char *d_chars, const std::vector<size_t> &offs) {
+	// d_chars: all sequences in HBM; pack them, count GC and separators.
+	const size_t n = ctx->n;
+	size_t words = 0;
+	ctx->word_off.resize(n);
+	for (size_t k = 0; k < n; k++) {
+		ctx->word_off[k] = words;
+		words += (plane_words(ctx->len[k]) + 1) & ~(size_t)1;  // keep 16-byte alignment
+	}
+	CK(dalloc(ctx, &ctx->pool_code, words));
+	CK(dalloc(ctx, &ctx->pool_spec, words));
+	unsigned long long *d_cnt = nullptr;
+	CK(dalloc(ctx, &d_cnt, 2 * n));
+	CK(cudaMemsetAsync(d_cnt, 0, 2 * n * sizeof(unsigned long long), ctx->stream));
+	for (size_t k = 0; k < n; k++) {
+		u32 nw = (u32)plane_words(ctx->len[k]);
+		k_pack<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(d_chars + offs[k], (u32)ctx->len[k],
+														   ctx->pool_code + ctx->word_off[k],
+														   ctx->pool_spec + ctx->word_off[k], nw, d_cnt + 2 * k);
+		ctx->st.esa_launches++;
+	}
+	std::vector<unsigned long long> cnt(2 * n);
+	CK(cudaMemcpyAsync(cnt.data(), d_cnt, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	dfree(ctx, d_cnt);
+	ctx->gc.resize(n), ctx->has_sep.resize(n);
+	std::vector<QueryView> qv(n);
+	for (size_t k = 0; k < n; k++) {
+		ctx->gc[k] = (double)cnt[2 * k] / (double)ctx->len[k];
+		ctx->has_sep[k] = cnt[2 * k + 1] != 0;
+		ctx->any_sep |= ctx->has_sep[k] != 0;
+		qv[k].t.code = ctx->pool_code + ctx->word_off[k];
+		qv[k].t.spec = ctx->pool_spec + ctx->word_off[k];
+		qv[k].t.len = (u32)ctx->len[k];
+		qv[k].t.mid = 0xffffffffu;
+		qv[k].has_sep = ctx->has_sep[k];
+	}
+	CK(dalloc(ctx, &ctx->d_queries, n));
+	CK(cudaMemcpyAsync(ctx->d_queries, qv.data(), n * sizeof(QueryView), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ANDI_OK;
+}
+
+static int pool_check(andi_ctx *ctx, const size_t *lens, size_t n) {
+	if (!ctx || !lens || n == 0) return ANDI_ERR_ARG;
+	for (size_t k = 0; k < n; k++) {
+		if (lens[k] == 0) {
+			ctx->err = "empty sequence";
+			return ANDI_ERR_ARG;
+		}
+		if (lens[k] > (size_t)(INT_MAX - 1) / 2) {
+			ctx->err = "sequence longer than (INT_MAX-1)/2";
+			return ANDI_ERR_TOO_LONG;
+		}
+	}
+	return ANDI_OK;
+}
+
+extern "C" int andi_pool_set_host(andi_ctx *ctx, const char *const *seqs, const size_t *lens, size_t n) {
+	if (!ctx || !seqs) return ANDI_ERR_ARG;
+	int rc = pool_check(ctx, lens, n);
+	if (rc) return rc;
+	CK(cudaSetDevice(ctx->device));
+	pool_release(ctx);
+	ctx->n = n;
+	ctx->len.assign(lens, lens + n);
+	std::vector<size_t> offs(n);
+	size_t total = 0;
+	for (size_t k = 0; k < n; k++) {
+		offs[k] = total;
+		total += (lens[k] + 15) & ~(size_t)15;
+	}
+	unsigned char *d_chars = nullptr;
+	CK(dalloc(ctx, &d_chars, total));
+	for (size_t k = 0; k < n; k++)
+		CK(cudaMemcpyAsync(d_chars + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, ctx->stream));
+	ctx->st.h2d_bytes += total;
+	rc = pool_finish(ctx, d_chars, offs);
+	dfree(ctx, d_chars);
+	return rc;
+}
+
+extern "C" int andi_pool_set_device(andi_ctx *ctx, const char *d_chars, const size_t *offsets,
+									const size_t *lens, size_t n) {
+	if (!ctx || !d_chars || !offsets) return ANDI_ERR_ARG;
+	int rc = pool_check(ctx, lens, n);
+	if (rc) return rc;
+	CK(cudaSetDevice(ctx->device));
+	pool_release(ctx);
+	ctx->n = n;
+	ctx->len.assign(lens, lens + n);
+	std::vector<size_t> offs(offsets, offsets + n);
+	return pool_finish(ctx, (const unsigned char *)d_chars, offs);
+}
+
+extern "C" size_t andi_pool_size(const andi_ctx *ctx) { return ctx ? ctx->n : 0; }
+
+extern "C" int andi_pool_info(const andi_ctx *ctx, size_t k, size_t *len, double *gc, int *has_separator) {
+	if (!ctx || k >= ctx->n) return ANDI_ERR_ARG;
+	if (len) *len = ctx->len[k];
+	if (gc) *gc = ctx->gc[k];
+	if (has_separator) *has_separator = ctx->has_sep[k];
+	return ANDI_OK;
+}
+
+// ------------------------------------------------------------------ index construction
+
+static TextView rs_view(const andi_esa *E) {
+	TextView t;
+	t.code = E->code, t.spec = E->spec, t.len = E->N, t.mid = E->n;
+	return t;
+}
+
+static int choose_depth(u32 N, u32 threshold) {
+	// directory depth ~ log4(N): about one suffix per bucket; never deeper than the anchor
+	// threshold (below it only the match LENGTH matters, see longest_match) nor than 14.
+	int k = (int)floor(log((double)N) / log(4.0) + 0.5);
+	k = std::max(k, 4);
+	k = std::min(k, 14);
+	if (threshold < (u32)k) k = (int)threshold;
+	return k >= 2 ? k : 0;
+}
+
+struct SortScratch {
+	u64 *keys_a = nullptr, *keys_b = nullptr;
+	u32 *vals_a = nullptr, *vals_b = nullptr;
+	u32 *v = nullptr, *g = nullptr, *grp = nullptr, *rank = nullptr, *pos_a = nullptr, *pos_b = nullptr;
+	unsigned char *amb = nullptr;
+	u32 *d_count = nullptr;
+	void *tmp = nullptr;
+	size_t tmp_bytes = 0;
+};
+
+struct MaxOp {
+	__host__ __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a > b ? a : b; }
+};
+
+static int build_suffix_array(andi_ctx *ctx, andi_esa *E) {
+	const u32 N = E->N;
+	cudaStream_t st = ctx->stream;
+	SortScratch s;
+	CK(dalloc(ctx, &s.keys_a, N));
+	CK(dalloc(ctx, &s.keys_b, N));
+	CK(dalloc(ctx, &s.vals_a, N));
+	CK(dalloc(ctx, &s.v, N));
+	CK(dalloc(ctx, &s.g, N));
+	CK(dalloc(ctx, &s.grp, N));
+	CK(dalloc(ctx, &s.rank, N));
+	CK(dalloc(ctx, &s.pos_a, N));
+	CK(dalloc(ctx, &s.amb, N));
+	CK(dalloc(ctx, &s.d_count, 1));
+	// CUB temp: the largest of the three primitives at size N
+	size_t b1 = 0, b2 = 0, b3 = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, b1, s.keys_a, s.keys_b, s.vals_a, E->SA, (int)N, 0, 64, st);
+	cub::DeviceScan::InclusiveScan(nullptr, b2, s.v, s.g, MaxOp(), (int)N, st);
+	cub::DeviceSelect::Flagged(nullptr, b3, s.pos_a, s.amb, s.pos_a, s.d_count, (int)N, st);
+	s.tmp_bytes = std::max(b1, std::max(b2, b3));
+	CK(cudaMallocAsync(&s.tmp, s.tmp_bytes, st));
+
+	TextView rs = rs_view(E);
+	// round 0: 16 characters, 48-bit keys, straight into SA
+	k_suffix_keys<<<nblocks(N, 256), 256, 0, st>>>(rs, s.keys_a, s.vals_a);
+	size_t tb = s.tmp_bytes;
+	CK(cub::DeviceRadixSort::SortPairs(s.tmp, tb, s.keys_a, s.keys_b, s.vals_a, E->SA, (int)N, 0, 48, st));
+	k_head_values<<<nblocks(N, 256), 256, 0, st>>>(s.keys_b, N, nullptr, s.v);
+	tb = s.tmp_bytes;
+	CK(cub::DeviceScan::InclusiveScan(s.tmp, tb, s.v, s.g, MaxOp(), (int)N, st));
+	k_apply_groups<<<nblocks(N, 256), 256, 0, st>>>(s.g, N, nullptr, E->SA, E->SA, s.grp, s.rank, s.amb);
+	k_iota<<<nblocks(N, 256), 256, 0, st>>>(s.v, N);
+	tb = s.tmp_bytes;
+	CK(cub::DeviceSelect::Flagged(s.tmp, tb, s.v, s.amb, s.pos_a, s.d_count, (int)N, st));
+	ctx->st.esa_launches += 8;
+	u32 m = 0;
+	CK(cudaMemcpyAsync(&m, s.d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+
+	if (m) {
+		CK(dalloc(ctx, &s.vals_b, m));
+		CK(dalloc(ctx, &s.pos_b, m));
+	}
+	for (u32 h = 16; m > 0; h *= 2) {
+		int bits = 33;
+		while (bits < 64 && (1ULL << (bits - 32)) <= (u64)N) bits++;  // group index needs log2(N) bits
+		k_round_keys<<<nblocks(m, 256), 256, 0, st>>>(s.pos_a, m, E->SA, s.grp, s.rank, h, N, s.keys_a, s.vals_a);
+		tb = s.tmp_bytes;
+		CK(cub::DeviceRadixSort::SortPairs(s.tmp, tb, s.keys_a, s.keys_b, s.vals_a, s.vals_b, (int)m, 0, bits, st));
+		k_head_values<<<nblocks(m, 256), 256, 0, st>>>(s.keys_b, m, s.pos_a, s.v);
+		tb = s.tmp_bytes;
+		CK(cub::DeviceScan::InclusiveScan(s.tmp, tb, s.v, s.g, MaxOp(), (int)m, st));
+		k_apply_groups<<<nblocks(m, 256), 256, 0, st>>>(s.g, m, s.pos_a, s.vals_b, E->SA, s.grp, s.rank, s.amb);
+		tb = s.tmp_bytes;
+		CK(cub::DeviceSelect::Flagged(s.tmp, tb, s.pos_a, s.amb, s.pos_b, s.d_count, (int)m, st));
+		ctx->st.esa_launches += 7;
+		ctx->st.sa_rounds++;
+		CK(cudaMemcpyAsync(&m, s.d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		std::swap(s.pos_a, s.pos_b);
+		if (h > N) break;
+	}
+	dfree(ctx, s.keys_a), dfree(ctx, s.keys_b), dfree(ctx, s.vals_a), dfree(ctx, s.vals_b);
+	dfree(ctx, s.v), dfree(ctx, s.g), dfree(ctx, s.grp), dfree(ctx, s.rank);
+	dfree(ctx, s.pos_a), dfree(ctx, s.pos_b), dfree(ctx, s.amb), dfree(ctx, s.d_count);
+	cudaFreeAsync(s.tmp, st);
+	return ANDI_OK;
+}
+
+static int build_lcp(andi_ctx *ctx, andi_esa *E) {
+	const u32 N = E->N;
+	cudaStream_t st = ctx->stream;
+	int32_t *phi = nullptr;
+	CK(dalloc(ctx, &phi, N));
+	TextView rs = rs_view(E);
+	k_phi<<<nblocks(N, 256), 256, 0, st>>>(E->SA, N, phi);
+	u32 slices = (N + 31) / 32;
+	if (E->has_sep)
+		k_plcp<true><<<nblocks(slices, 128), 128, 0, st>>>(rs, phi);
+	else
+		k_plcp<false><<<nblocks(slices, 128), 128, 0, st>>>(rs, phi);
+	k_lcp_from_plcp<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(E->SA, phi, N, E->LCP);
+	ctx->st.esa_launches += 3;
+	dfree(ctx, phi);
+	return ANDI_OK;
+}
+
+static int build_directory(andi_ctx *ctx, andi_esa *E) {
+	cudaStream_t st = ctx->stream;
+	const int K = E->K;
+	if (K == 0) return ANDI_OK;
+	const size_t entries = ((size_t)1 << (2 * K)) + 1;
+	CK(dalloc(ctx, &E->dir, entries));
+	TextView rs = rs_view(E);
+	k_fill_u32<<<std::min<unsigned>(nblocks(entries, 256), 4096u), 256, 0, st>>>(E->dir, entries, E->N);
+	if (E->has_sep)
+		k_dir_heads<true><<<nblocks(E->N, 256), 256, 0, st>>>(rs, E->SA, K, E->dir);
+	else
+		k_dir_heads<false><<<nblocks(E->N, 256), 256, 0, st>>>(rs, E->SA, K, E->dir);
+	// presence bitmaps, levels 1 .. K-1
+	size_t words = 0;
+	for (int m = 1; m < K; m++) {
+		E->present.offset[m] = (u32)words;
+		words += (((size_t)1 << (2 * m)) + 31) / 32;
+	}
+	CK(dalloc(ctx, &E->present.bits, words));
+	u32 top_bits = 1u << (2 * (K - 1));
+	k_presence_from_dir<<<nblocks((top_bits + 31) / 32, 256), 256, 0, st>>>(E->dir, top_bits,
+																			 E->present.bits + E->present.offset[K - 1]);
+	for (int m = K - 2; m >= 1; m--) {
+		u32 nb = 1u << (2 * m);
+		k_presence_down<<<nblocks((nb + 31) / 32, 256), 256, 0, st>>>(E->present.bits + E->present.offset[m + 1], nb,
+																	   E->present.bits + E->present.offset[m]);
+	}
+	k_presence_patch<<<nblocks(E->N, 256), 256, 0, st>>>(rs, K, E->present);
+	ctx->st.esa_launches += 3 + (K - 1);
+	return ANDI_OK;
+}
+
+static int build_full(andi_ctx *ctx, andi_esa *E) {
+	// CLD, FVC, prefix cache: only for the reference-visible esa_s (ANDI_ESA_FULL)
+	cudaStream_t st = ctx->stream;
+	const u32 N = E->N;
+	CK(dalloc(ctx, &E->CLD, (size_t)N + 1));
+	CK(dalloc(ctx, &E->FVC, (size_t)N));
+	CK(dalloc(ctx, &E->cache, (size_t)1 << 20));
+	TextView rs = rs_view(E);
+	k_fvc<<<nblocks(N, 256), 256, 0, st>>>(rs, E->SA, E->LCP, E->FVC);
+	MinPyramid P{};
+	P.level[0] = E->LCP;
+	P.size[0] = N + 1;
+	P.levels = 1;
+	std::vector<int32_t *> owned;
+	while (P.size[P.levels - 1] > 32) {
+		u32 ns = (P.size[P.levels - 1] + 31) / 32;
+		int32_t *buf = nullptr;
+		CK(dalloc(ctx, &buf, ns));
+		owned.push_back(buf);
+		k_min_reduce32<<<nblocks(ns, 256), 256, 0, st>>>(P.level[P.levels - 1], P.size[P.levels - 1], buf, ns);
+		P.level[P.levels] = buf;
+		P.size[P.levels] = ns;
+		P.levels++;
+		ctx->st.esa_launches++;
+	}
+	k_cld<<<nblocks(N, 256), 256, 0, st>>>(P, N, E->CLD);
+	for (auto b : owned) cudaFreeAsync(b, st);
+	EsaView V;
+	V.rs = rs, V.SA = E->SA, V.LCP = E->LCP, V.CLD = E->CLD, V.FVC = E->FVC;
+	k_prefix_cache<<<nblocks(1u << 20, 128), 128, 0, st>>>(V, E->cache);
+	ctx->st.esa_launches += 3;
+	E->full = true;
+	return ANDI_OK;
+}
+
+static void esa_release(andi_esa *E) {
+	andi_ctx *ctx = E->ctx;
+	dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->SA), dfree(ctx, E->LCP);
+	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
+	dfree(ctx, E->cache);
+}
+
+// RS planes are in place; build everything else.
+static int build_index(andi_ctx *ctx, andi_esa *E, unsigned flags) {
+	cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+	mark(ctx, e0);
+	if (!ctx->first_ev) {
+		ctx->first_ev = get_event(ctx);
+		mark(ctx, ctx->first_ev);
+	}
+	CK(dalloc(ctx, &E->SA, E->N));
+	CK(dalloc(ctx, &E->LCP, (size_t)E->N + 1));
+	int rc = build_suffix_array(ctx, E);
+	if (!rc) rc = build_lcp(ctx, E);
+	if (!rc) rc = build_directory(ctx, E);
+	if (!rc && (flags & ANDI_ESA_FULL)) rc = build_full(ctx, E);
+	mark(ctx, e1);
+	ctx->esa_ev.emplace_back(e0, e1);
+	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);
+	mark(ctx, ctx->last_ev);
+	ctx->st.subjects++;
+	if (!rc) {
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) {
+			ctx->err = std::string("index kernels: ") + cudaGetErrorString(e);
+			rc = ANDI_ERR_CUDA;
+		}
+	}
+	return rc;
+}
+
+extern "C" int andi_esa_build(andi_ctx *ctx, size_t subject, unsigned flags, andi_esa **out) {
+	if (!ctx || !out || subject >= ctx->n) return ANDI_ERR_ARG;
+	*out = nullptr;
+	CK(cudaSetDevice(ctx->device));
+	andi_esa *E = new andi_esa();
+	E->ctx = ctx;
+	E->n = (u32)ctx->len[subject];
+	E->N = 2 * E->n + 1;
+	E->has_sep = ctx->has_sep[subject] != 0;
+	E->self = (u32)subject;
+	size_t nw = plane_words(E->N);
+	if (dalloc(ctx, &E->code, nw) != cudaSuccess || dalloc(ctx, &E->spec, nw) != cudaSuccess) {
+		ctx->err = "device allocation failed";
+		esa_release(E);
+		delete E;
+		return ANDI_ERR_NOMEM;
+	}
+	k_build_rs<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(ctx->pool_code + ctx->word_off[subject],
+														   ctx->pool_spec + ctx->word_off[subject], E->n, E->code,
+														   E->spec, (u32)nw);
+	ctx->st.esa_launches++;
+	*out = E;
+	// The directory depth is tied to the default threshold (p = 0.025); a walk that is given a
+	// smaller threshold falls back to the generic search (see launch sites).
+	E->threshold = (u32)andi_threshold(0.025, ctx->gc[subject], E->N);
+	E->K = choose_depth(E->N, E->threshold);
+	int rc = ANDI_OK;
+	rc = build_index(ctx, E, flags);
+	if (rc) {
+		esa_release(E);
+		delete E;
+		*out = nullptr;
+	}
+	return rc;
+}
+
+extern "C" int andi_esa_build_rs(andi_ctx *ctx, const char *rs, size_t rs_len, unsigned flags, andi_esa **out) {
+	if (!ctx || !rs || !out) return ANDI_ERR_ARG;
+	*out = nullptr;
+	if (rs_len == 0 || rs_len > (size_t)INT_MAX) {
+		ctx->err = "bad RS length";
+		return ANDI_ERR_TOO_LONG;
+	}
+	CK(cudaSetDevice(ctx->device));
+	andi_esa *E = new andi_esa();
+	E->ctx = ctx;
+	E->N = (u32)rs_len;
+	E->n = (u32)(rs_len / 2);
+	size_t nw = plane_words(E->N);
+	unsigned char *d_chars = nullptr;
+	unsigned long long *d_cnt = nullptr;
+	unsigned long long cnt[2] = {0, 0};
+	cudaError_t e = cudaSuccess;
+	if ((e = dalloc(ctx, &E->code, nw)) != cudaSuccess || (e = dalloc(ctx, &E->spec, nw)) != cudaSuccess ||
+		(e = dalloc(ctx, &d_chars, rs_len)) != cudaSuccess || (e = dalloc(ctx, &d_cnt, 2)) != cudaSuccess) {
+		ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(e);
+		esa_release(E);
+		delete E;
+		return ANDI_ERR_NOMEM;
+	}
+	cudaMemcpyAsync(d_chars, rs, rs_len, cudaMemcpyHostToDevice, ctx->stream);
+	cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), ctx->stream);
+	ctx->st.h2d_bytes += rs_len;
+	k_pack_rs_bytes<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(d_chars, E->N, E->code, E->spec, (u32)nw, d_cnt);
+	ctx->st.esa_launches++;
+	cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream);
+	e = cudaStreamSynchronize(ctx->stream);
+	dfree(ctx, d_chars), dfree(ctx, d_cnt);
+	if (e != cudaSuccess) {
+		ctx->err = std::string("pack RS: ") + cudaGetErrorString(e);
+		esa_release(E);
+		delete E;
+		return ANDI_ERR_CUDA;
+	}
+	// A general RS string may hold '#' anywhere (or not at all); the SPEC path makes no
+	// assumption about it, so use it unless the string has the canonical shape.
+	E->has_sep = cnt[1] != 0 || (rs_len % 2 == 0) || rs[rs_len / 2] != '#';
+	// gc of the forward half for the default threshold
+	size_t gcn = 0;
+	for (size_t k = E->n + 1; k < rs_len; k++) gcn += (rs[k] == 'G' || rs[k] == 'C');
+	double gc = E->n ? (double)gcn / (double)E->n : 0.5;
+	E->threshold = (u32)andi_threshold(0.025, gc, E->N);
+	E->K = choose_depth(E->N, E->threshold);
+	int rc = build_index(ctx, E, flags);
+	if (rc) {
+		esa_release(E);
+		delete E;
+		return rc;
+	}
+	*out = E;
+	return ANDI_OK;
+}
+
+extern "C" void andi_esa_free(andi_esa *E) {
+	if (!E) return;
+	cudaSetDevice(E->ctx->device);
+	esa_release(E);
+	delete E;
+}
+
+extern "C" int32_t andi_esa_len(const andi_esa *E) { return E ? (int32_t)E->N : 0; }
+
+extern "C" int andi_esa_download(const andi_esa *E, int32_t *SA, int32_t *LCP, int32_t *CLD, char *FVC,
+								 andi_lcp_inter *cache) {
+	if (!E) return ANDI_ERR_ARG;
+	andi_ctx *ctx = E->ctx;
+	CK(cudaSetDevice(ctx->device));
+	if ((CLD || FVC || cache) && !E->full) {
+		ctx->err = "CLD/FVC/cache need ANDI_ESA_FULL";
+		return ANDI_ERR_ARG;
+	}
+	cudaStream_t st = ctx->stream;
+	const size_t N = E->N;
+	if (SA) CK(cudaMemcpyAsync(SA, E->SA, N * 4, cudaMemcpyDeviceToHost, st));
+	if (LCP) CK(cudaMemcpyAsync(LCP, E->LCP, (N + 1) * 4, cudaMemcpyDeviceToHost, st));
+	if (CLD) CK(cudaMemcpyAsync(CLD, E->CLD, (N + 1) * 4, cudaMemcpyDeviceToHost, st));
+	if (FVC) CK(cudaMemcpyAsync(FVC, E->FVC, N, cudaMemcpyDeviceToHost, st));
+	if (cache) CK(cudaMemcpyAsync(cache, E->cache, sizeof(Inter) << 20, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	ctx->st.d2h_bytes += (SA ? N * 4 : 0) + (LCP ? (N + 1) * 4 : 0) + (CLD ? (N + 1) * 4 : 0) + (FVC ? N : 0) +
+						 (cache ? (sizeof(Inter) << 20) : 0);
+	return ANDI_OK;
+}
+
+static SubjectIndex subject_index(const andi_esa *E) {
+	SubjectIndex S;
+	S.rs = rs_view(E);
+	S.SA = E->SA, S.LCP = E->LCP, S.dir = E->dir, S.present = E->present;
+	S.K = E->K, S.threshold = E->threshold, S.self = E->self, S.has_sep = E->has_sep;
+	return S;
+}
+
+// Upload + pack a list of host strings as temporary queries.
+struct TempQueries {
+	u64 *code = nullptr, *spec = nullptr;
+	QueryView *d_views = nullptr;
+	bool any_sep = false;
+};
+
+static int temp_queries(andi_ctx *ctx, const char *const *qs, const size_t *lens, size_t nq, TempQueries &T) {
+	std::vector<size_t> coff(nq), woff(nq);
+	size_t chars = 0, words = 0;
+	for (size_t k = 0; k < nq; k++) {
+		coff[k] = chars, woff[k] = words;
+		chars += (lens[k] + 15) & ~(size_t)15;
+		words += (plane_words(lens[k]) + 1) & ~(size_t)1;
+	}
+	unsigned char *d_chars = nullptr;
+	unsigned long long *d_cnt = nullptr;
+	CK(dalloc(ctx, &d_chars, chars));
+	CK(dalloc(ctx, &d_cnt, 2));
+	CK(dalloc(ctx, &T.code, words));
+	CK(dalloc(ctx, &T.spec, words));
+	CK(dalloc(ctx, &T.d_views, nq));
+	CK(cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
+	std::vector<QueryView> qv(nq);
+	for (size_t k = 0; k < nq; k++) {
+		if (lens[k]) CK(cudaMemcpyAsync(d_chars + coff[k], qs[k], lens[k], cudaMemcpyHostToDevice, ctx->stream));
+		u32 nw = (u32)plane_words(lens[k]);
+		k_pack<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(d_chars + coff[k], (u32)lens[k], T.code + woff[k],
+														   T.spec + woff[k], nw, d_cnt);
+		qv[k].t.code = T.code + woff[k], qv[k].t.spec = T.spec + woff[k];
+		qv[k].t.len = (u32)lens[k], qv[k].t.mid = 0xffffffffu, qv[k].has_sep = 0;
+	}
+	ctx->st.h2d_bytes += chars;
+	unsigned long long cnt[2];
+	CK(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(T.d_views, qv.data(), nq * sizeof(QueryView), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	T.any_sep = cnt[1] != 0;
+	dfree(ctx, d_chars), dfree(ctx, d_cnt);
+	return ANDI_OK;
+}
+
+static void temp_release(andi_ctx *ctx, TempQueries &T) {
+	dfree(ctx, T.code), dfree(ctx, T.spec), dfree(ctx, T.d_views);
+}
+
+extern "C" int andi_esa_get_match(const andi_esa *E, const char *const *queries, const size_t *lens, size_t nq,
+								  andi_lcp_inter *out) {
+	if (!E || !queries || !lens || !out) return ANDI_ERR_ARG;
+	if (nq == 0) return ANDI_OK;
+	andi_ctx *ctx = E->ctx;
+	CK(cudaSetDevice(ctx->device));
+	TempQueries T;
+	int rc = temp_queries(ctx, queries, lens, nq, T);
+	if (rc) return rc;
+	Inter *d_out = nullptr;
+	CK(dalloc(ctx, &d_out, nq));
+	SubjectIndex S = subject_index(E);
+	if (E->has_sep || T.any_sep)
+		k_get_match<true><<<nblocks(nq, 128), 128, 0, ctx->stream>>>(S, T.d_views, (u32)nq, d_out);
+	else
+		k_get_match<false><<<nblocks(nq, 128), 128, 0, ctx->stream>>>(S, T.d_views, (u32)nq, d_out);
+	CK(cudaMemcpyAsync(out, d_out, nq * sizeof(Inter), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	dfree(ctx, d_out);
+	temp_release(ctx, T);
+	return ANDI_OK;
+}
+
+// ------------------------------------------------------------------ the walk
+
+typedef void (*walk_fn)(const SubjectIndex *, u32, const QueryView *, const u32 *, u32, u32, u32 *,
+						unsigned long long *);
+
+static walk_fn pick_walk(int model, bool spec) {
+	bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
+	if (quarter) return spec ? k_walk<true, true> : k_walk<true, false>;
+	return spec ? k_walk<false, true> : k_walk<false, false>;
+}
+
+// Launch the walk for `nslots` subject indexes against nq queries; d_out gets nslots*nq cells.
+static int launch_walk(andi_ctx *ctx, const SubjectIndex *d_subjects, u32 nslots, const QueryView *d_queries,
+					   const u32 *d_query_ids, u32 nq, u32 threshold_override, int model, bool spec, u32 *d_out,
+					   unsigned long long *d_counter) {
+	walk_fn fn = pick_walk(model, spec);
+	int per_sm = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+	if (per_sm < 1) per_sm = 1;
+	unsigned long long total = (unsigned long long)nslots * nq;
+	unsigned grid = (unsigned)std::min<unsigned long long>((total + 255) / 256,
+															(unsigned long long)per_sm * ctx->sm_count);
+	CK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), ctx->stream));
+	cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+	mark(ctx, e0);
+	if (!ctx->first_ev) {
+		ctx->first_ev = get_event(ctx);
+		mark(ctx, ctx->first_ev);
+	}
+	fn<<<grid, 256, 0, ctx->stream>>>(d_subjects, nslots, d_queries, d_query_ids, nq, threshold_override, d_out,
+									   d_counter);
+	mark(ctx, e1);
+	ctx->walk_ev.emplace_back(e0, e1);
+	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);
+	mark(ctx, ctx->last_ev);
+	ctx->st.walk_launches++;
+	ctx->st.pairs += total;
+	CK(cudaGetLastError());
+	return ANDI_OK;
+}
+
+extern "C" int andi_dist_row(andi_ctx *ctx, const andi_esa *E, const size_t *query_ids, size_t nq,
+							 size_t threshold, int model, andi_model *out) {
+	if (!ctx || !E || !query_ids || !out || E->ctx != ctx) return ANDI_ERR_ARG;
+	if (nq == 0) return ANDI_OK;
+	CK(cudaSetDevice(ctx->device));
+	std::vector<u32> ids(nq);
+	bool spec = E->has_sep;
+	for (size_t k = 0; k < nq; k++) {
+		if (query_ids[k] >= ctx->n) return ANDI_ERR_ARG;
+		ids[k] = (u32)query_ids[k];
+		spec |= ctx->has_sep[ids[k]] != 0;
+	}
+	SubjectIndex S = subject_index(E);
+	S.self = 0xffffffffu;  // dist_anchor itself has no notion of "self"
+	if (threshold < (size_t)S.K) S.K = 0;  // directory assumes K <= threshold
+	SubjectIndex *d_S = nullptr;
+	u32 *d_ids = nullptr, *d_out = nullptr;
+	unsigned long long *d_counter = nullptr;
+	CK(dalloc(ctx, &d_S, 1));
+	CK(dalloc(ctx, &d_ids, nq));
+	CK(dalloc(ctx, &d_out, nq * 17));
+	CK(dalloc(ctx, &d_counter, 1));
+	CK(cudaMemcpyAsync(d_S, &S, sizeof S, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(d_ids, ids.data(), nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+	int rc = launch_walk(ctx, d_S, 1, ctx->d_queries, d_ids, (u32)nq, (u32)threshold, model, spec, d_out, d_counter);
+	if (!rc) {
+		CK(cudaMemcpyAsync(out, d_out, nq * sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		ctx->st.d2h_bytes += nq * sizeof(andi_model);
+		harvest_events(ctx);
+	}
+	dfree(ctx, d_S), dfree(ctx, d_ids), dfree(ctx, d_out), dfree(ctx, d_counter);
+	return rc;
+}
+
+extern "C" int andi_dist_anchor(andi_ctx *ctx, const andi_esa *E, const char *query, size_t qlen,
+								size_t threshold, int model, andi_model *out) {
+	if (!ctx || !E || !query || !out || E->ctx != ctx) return ANDI_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	if (qlen == 0) {
+		memset(out, 0, sizeof *out);
+		return ANDI_OK;
+	}
+	TempQueries T;
+	int rc = temp_queries(ctx, &query, &qlen, 1, T);
+	if (rc) return rc;
+	SubjectIndex S = subject_index(E);
+	S.self = 0xffffffffu;
+	if (threshold < (size_t)S.K) S.K = 0;
+	SubjectIndex *d_S = nullptr;
+	u32 *d_out = nullptr;
+	unsigned long long *d_counter = nullptr;
+	CK(dalloc(ctx, &d_S, 1));
+	CK(dalloc(ctx, &d_out, 17));
+	CK(dalloc(ctx, &d_counter, 1));
+	CK(cudaMemcpyAsync(d_S, &S, sizeof S, cudaMemcpyHostToDevice, ctx->stream));
+	rc = launch_walk(ctx, d_S, 1, T.d_views, nullptr, 1, (u32)threshold, model, E->has_sep || T.any_sep, d_out,
+					 d_counter);
+	if (!rc) {
+		CK(cudaMemcpyAsync(out, d_out, sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		ctx->st.d2h_bytes += sizeof(andi_model);
+		harvest_events(ctx);
+	}
+	dfree(ctx, d_S), dfree(ctx, d_out), dfree(ctx, d_counter);
+	temp_release(ctx, T);
+	return rc;
+}
+
+extern "C" int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
+							  int low_memory, andi_model *out) {
+	if (!ctx || !out || s_begin > s_end || s_end > ctx->n) return ANDI_ERR_ARG;
+	if (s_begin == s_end) return ANDI_OK;
+	CK(cudaSetDevice(ctx->device));
+	const size_t n = ctx->n;
+	// Subjects per walk launch: enough pairs in flight to fill the GPU (one thread per pair),
+	// bounded by a memory budget for resident indexes; 1 in low-memory mode.
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	size_t maxlen = 0;
+	for (size_t i = s_begin; i < s_end; i++) maxlen = std::max(maxlen, ctx->len[i]);
+	size_t per_index = (2 * maxlen + 2) * 9 + ((size_t)4 << 24) + (64u << 20);
+	size_t want_pairs = (size_t)ctx->sm_count * 2048;
+	size_t batch = low_memory ? 1 : std::max<size_t>(1, (want_pairs + n - 1) / n);
+	batch = std::min(batch, std::max<size_t>(1, (free_b / 2) / per_index));
+	batch = std::min(batch, s_end - s_begin);
+
+	SubjectIndex *d_S = nullptr;
+	u32 *d_out = nullptr;
+	unsigned long long *d_counter = nullptr;
+	CK(dalloc(ctx, &d_S, batch));
+	CK(dalloc(ctx, &d_out, batch * n * 17));
+	CK(dalloc(ctx, &d_counter, 1));
+	std::vector<SubjectIndex> hS(batch);
+	std::vector<andi_esa *> live;
+	int rc = ANDI_OK;
+	for (size_t b0 = s_begin; b0 < s_end && !rc; b0 += batch) {
+		size_t b1 = std::min(b0 + batch, s_end);
+		bool spec = ctx->any_sep;
+		for (size_t i = b0; i < b1 && !rc; i++) {
+			andi_esa *E = new andi_esa();
+			E->ctx = ctx;
+			E->n = (u32)ctx->len[i];
+			E->N = 2 * E->n + 1;
+			E->has_sep = ctx->has_sep[i] != 0;
+			E->self = (u32)i;
+			E->threshold = (u32)andi_threshold(p_value, ctx->gc[i], E->N);
+			E->K = choose_depth(E->N, E->threshold);
+			size_t nw = plane_words(E->N);
+			live.push_back(E);
+			if (dalloc(ctx, &E->code, nw) != cudaSuccess || dalloc(ctx, &E->spec, nw) != cudaSuccess) {
+				ctx->err = "device allocation failed";
+				rc = ANDI_ERR_NOMEM;
+				break;
+			}
+			k_build_rs<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(ctx->pool_code + ctx->word_off[i],
+																   ctx->pool_spec + ctx->word_off[i], E->n, E->code,
+																   E->spec, (u32)nw);
+			ctx->st.esa_launches++;
+			rc = build_index(ctx, E, ANDI_ESA_SEARCH);
+			hS[i - b0] = subject_index(E);
+		}
+		if (!rc) {
+			CK(cudaMemcpyAsync(d_S, hS.data(), (b1 - b0) * sizeof(SubjectIndex), cudaMemcpyHostToDevice, ctx->stream));
+			rc = launch_walk(ctx, d_S, (u32)(b1 - b0), ctx->d_queries, nullptr, (u32)n, 0, model, spec, d_out,
+							 d_counter);
+		}
+		if (!rc) {
+			CK(cudaMemcpyAsync(out + (b0 - s_begin) * n, d_out, (b1 - b0) * n * sizeof(andi_model),
+							   cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaStreamSynchronize(ctx->stream));
+			ctx->st.d2h_bytes += (b1 - b0) * n * sizeof(andi_model);
+		}
+		for (auto E : live) {
+			esa_release(E);
+			delete E;
+		}
+		live.clear();
+	}
+	cudaStreamSynchronize(ctx->stream);
+	harvest_events(ctx);
+	dfree(ctx, d_S), dfree(ctx, d_out), dfree(ctx, d_counter);
+	return rc;
+}

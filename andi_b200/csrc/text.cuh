@@ -1,0 +1,92 @@
+// andi_b200/csrc/text.cuh -- packed-text device helpers shared by every kernel.
+//
+// Text layout in HBM (both for pool sequences and for RS = revcomp '#' forward):
+//   code plane  u64 words, 32 characters per word, 2 bits each, character c of a word at
+//               bits [2*(c&31), 2*(c&31)+2).  A=0 C=1 G=2 T=3 (nucl2bit, src/model.c:295-299).
+//   spec plane  same geometry; 01 where the character is not a nucleotide. For those the code
+//               plane holds 0 for '!', 1 for '#', 2 for ';'.
+// Byte equality of the reference (`S[a] == Q[b]`, src/process.c:59-65, src/esa.c:408,546,592)
+// is therefore "code pair equal and spec pair equal", and the byte order the suffix array
+// is built under ('\0' < '!' < '#' < ';' < A < C < G < T) is sym3() below.
+// Every plane is allocated with two zero guard words so a 32-character window may start at
+// any position up to and including the text length.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+
+#define ANDI_EVEN_BITS 0x5555555555555555ULL
+
+struct TextView {
+	const u64 *code;
+	const u64 *spec;
+	u32 len;  // characters
+	u32 mid;  // RS only: index of '#' (== forward length n); 0xffffffff for plain sequences
+};
+
+// 32 characters starting at pos (character 0 in the low bits).
+__device__ __forceinline__ u64 window32(const u64 *__restrict__ w, u32 pos) {
+	u32 i = pos >> 5, sh = (pos & 31u) * 2u;
+	u64 a = __ldg(w + i);
+	if (sh == 0) return a;
+	u64 b = __ldg(w + i + 1);
+	return (a >> sh) | (b << (64u - sh));
+}
+
+__device__ __forceinline__ u32 code_at(const u64 *__restrict__ w, u32 pos) {
+	return (u32)(__ldg(w + (pos >> 5)) >> ((pos & 31u) * 2u)) & 3u;
+}
+
+// Length of the common prefix of a[pa..] and b[pb..], at most `limit` characters.
+// SPEC=false ignores the spec planes: the caller guarantees that no separator lies inside
+// either range (it cuts `limit` at '#', and neither text contains '!' / ';').
+template <bool SPEC>
+__device__ __forceinline__ u32 match_len(const TextView &a, u32 pa, const TextView &b, u32 pb,
+										 u32 limit) {
+	u32 k = 0;
+	while (k < limit) {
+		u64 x = window32(a.code, pa + k) ^ window32(b.code, pb + k);
+		if (SPEC) x |= window32(a.spec, pa + k) ^ window32(b.spec, pb + k);
+		x = (x | (x >> 1)) & ANDI_EVEN_BITS;
+		if (x) {
+			k += (u32)(__ffsll((long long)x) - 1) >> 1;
+			return k < limit ? k : limit;
+		}
+		k += 32;
+	}
+	return limit;
+}
+
+// Rank of the character at pos in the reference's byte order; 0 past the end.
+// For RS in SPEC=false mode the only separator is '#' at t.mid.
+template <bool SPEC>
+__device__ __forceinline__ u32 sym3(const TextView &t, u32 pos) {
+	if (pos >= t.len) return 0;
+	u32 c = code_at(t.code, pos);
+	if (SPEC) {
+		u32 s = code_at(t.spec, pos) & 1u;
+		return s ? c + 1 : c + 4;
+	}
+	return pos == t.mid ? 2u : c + 4;
+}
+
+// How far a comparison that starts at RS position p may run before it hits '#' or the end.
+// SPEC=true lets the planes decide, so only the end counts.
+template <bool SPEC>
+__device__ __forceinline__ u32 rs_run(const TextView &rs, u32 p) {
+	if (SPEC) return rs.len - p;
+	if (p < rs.mid) return rs.mid - p;
+	if (p == rs.mid) return 0;
+	return rs.len - p;
+}
+
+// First k characters (k <= 16) of a window as an integer with the FIRST character most
+// significant, i.e. monotone in lexicographic order. Used as k-mer directory key.
+__device__ __forceinline__ u32 kmer_key(u64 win, int k) {
+	u32 w = (u32)win;							  // 16 characters
+	w = __brev(w);								  // character order reversed, bits inside pairs swapped
+	w = ((w >> 1) & 0x55555555u) | ((w & 0x55555555u) << 1);
+	return k >= 16 ? w : (w >> (32 - 2 * k));
+}

@@ -1,0 +1,157 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle on the same inputs.
+Integer work: every comparison is bit-exact."""
+import gzip
+import json
+import random
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from andi_b200 import native, synth
+from conftest import stress_sequences
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = native.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return json.loads((G / "golden.json").read_text())
+
+
+def _esa_cases(esa_fixtures):
+    groups = stress_sequences()
+    cases = list(esa_fixtures)
+    for name in ("subst", "join", "repeat", "short", "lowent", "indel"):
+        cases.extend(groups[name])
+    return cases
+
+
+def test_esa_arrays_bit_identical(ctx, esa_fixtures):
+    """E1-E5: SA, LCP, CLD, FVC and the 4^10 prefix cache equal the oracle's (= the reference's)."""
+    cases = _esa_cases(esa_fixtures)
+    ctx.set_pool(cases)
+    for k, s in enumerate(cases):
+        o = oracle.OracleEsa(s)
+        e = ctx.esa_build(k, full=True)
+        got = e.download(full=True)
+        assert np.array_equal(got["SA"], o.array("SA")), ("SA", k)
+        assert np.array_equal(got["LCP"], o.array("LCP")), ("LCP", k)
+        assert np.array_equal(got["FVC"], o.array("FVC")), ("FVC", k)
+        assert np.array_equal(got["CLD"][:-1], o.array("CLD")[:-1]), ("CLD", k)
+        assert np.array_equal(got["cache"], o.array("cache")), ("cache", k)
+        e.free(), o.close()
+
+
+def test_esa_from_rs_string_matches_golden(ctx, golden):
+    """esa_init's own calling convention (an RS string) against the reference's arrays."""
+    for ent in golden["esa"]:
+        e = ctx.esa_build_rs(ent["rs"].encode(), full=True)
+        got = e.download(full=True)
+        assert got["SA"].tolist() == ent["SA"]
+        assert got["LCP"].tolist() == ent["LCP"]
+        assert got["FVC"].tolist() == ent["FVC"]
+        assert got["CLD"][:-1].tolist() == ent["CLD"]
+        qs = [q.encode() for q in ent["queries"]]
+        m = e.get_match(qs)
+        assert m[:, :3].tolist() == ent["get_match"]
+        e.free()
+
+
+def test_get_match_spec(ctx, esa_fixtures):
+    """E6: longest prefix match and its exact SA range, against the oracle's spec search."""
+    rng = random.Random(7)
+    groups = stress_sequences()
+    cases = list(esa_fixtures) + groups["join"][:2] + groups["repeat"][:1] + groups["subst"][:1] + groups["lowent"][:1]
+    ctx.set_pool(cases)
+    for k, s in enumerate(cases):
+        o = oracle.OracleEsa(s)
+        rs = o.rs
+        qs = []
+        for _ in range(3000):
+            ln = rng.choice([1, 2, 5, 9, 10, 11, 12, 13, 17, 25, 40, 90])
+            r = rng.random()
+            if r < 0.6:
+                p = rng.randrange(0, len(rs) - 1)
+                q = bytearray(rs[p : p + ln].replace(b"#", b"A").replace(b";", b"!"))
+                if q and rng.random() < 0.5:
+                    q[rng.randrange(len(q))] = rng.choice(b"ACGT")
+                q = bytes(q)
+            else:
+                q = bytes(rng.choice(b"ACGT") for _ in range(ln))
+            if q:
+                qs.append(q)
+        e = ctx.esa_build(k)
+        got = e.get_match(qs)
+        for q, g in zip(qs, got):
+            assert tuple(g[:3]) == o.get_match(q, "spec")[:3], (k, q)
+        e.free(), o.close()
+
+
+@pytest.mark.parametrize("model", ["JC", "LOGDET", "RAW", "KIMURA", "ANI"])
+def test_rows_match_oracle_on_stress_sets(ctx, model):
+    """P1-P4, M1, M2, D1: whole rows of the matrix, every corner case group."""
+    for name, seqs in stress_sequences().items():
+        ctx.set_pool(seqs)
+        got = ctx.dist_rows(model=model)
+        want = oracle.rows(seqs, model)
+        assert np.array_equal(got, want), (name, model)
+        low = ctx.dist_rows(model=model, low_memory=True)  # test/test_extra.sh:19-22
+        assert np.array_equal(low, want), (name, model, "low-memory")
+
+
+def test_config1_known_answer(ctx, golden):
+    """BASELINE.json configs[0]: the survey's known-answer vector, from the committed FASTA."""
+    fa = gzip.open(G / "c1.fa.gz").read()
+    seqs = [s for _, s in oracle.parse_fasta(fa)]
+    ctx.set_pool(seqs)
+    for model in ("JC", "LOGDET", "RAW"):
+        got = ctx.dist_rows(model=model).reshape(-1, 17)
+        assert np.array_equal(got, np.array(golden["c1"][model], dtype=np.uint32)), model
+    # legacy call shapes: one index, explicit query ids / one host query string
+    e = ctx.esa_build(0)
+    t = native.threshold(0.025, ctx.pool_info(0)[1], 2 * len(seqs[0]) + 1)
+    assert t == golden["c1_threshold"]
+    row = ctx.dist_row(e, [1], t, "JC")
+    assert row[0].tolist() == golden["c1"]["JC"][1]
+    one = ctx.dist_anchor(e, seqs[1], t, "JC")
+    assert one.tolist() == golden["c1"]["JC"][1]
+    e.free()
+
+
+def test_p_value_and_explicit_threshold(ctx):
+    seqs = stress_sequences()["subst"]
+    ctx.set_pool(seqs)
+    for p in (0.1, 0.001):
+        assert np.array_equal(ctx.dist_rows(p_value=p), oracle.rows(seqs, "JC", p_value=p))
+    o = oracle.OracleEsa(seqs[0])
+    e = ctx.esa_build(0)
+    for t in (5, 9, 14, 30):  # below / above the directory depth
+        assert np.array_equal(ctx.dist_anchor(e, seqs[2], t, "JC"), o.dist_anchor(seqs[2], t, "JC", spec=True)), t
+    e.free(), o.close()
+
+
+def test_medium_genomes_with_properties(ctx):
+    """1 Mbp genomes: parity with the oracle plus size-independent properties."""
+    seqs = synth.star_phylogeny(4, 1_000_000, [0.0, 0.005, 0.02, 0.05], seed=2024)
+    ctx.set_pool(seqs)
+    got = ctx.dist_rows()
+    want = oracle.rows(seqs, "JC", s_begin=0, s_end=2)
+    assert np.array_equal(got[:2], want)
+    tot = got[:, :, :16].sum(axis=2)
+    assert (got[:, :, 16] >= tot)[~np.eye(4, dtype=bool)].all()  # covered <= query length
+    # reverse-complementing a query must not change its row entries' totals (both strands indexed)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    seqs_rc = [seqs[0]] + [s.translate(comp)[::-1] for s in seqs[1:]]
+    ctx.set_pool(seqs_rc)
+    got_rc = ctx.dist_rows(s_begin=0, s_end=1)
+    assert np.array_equal(got_rc[0, 1:, :16].sum(axis=1), got[0, 1:, :16].sum(axis=1))
