@@ -398,7 +398,8 @@ static int build_suffix_array(andi_ctx *ctx, andi_esa *E) {
 	k_iota<<<nblocks(N, 256), 256, 0, st>>>(s.v, N);
 	tb = s.tmp_bytes;
 	CK(cub::DeviceSelect::Flagged(s.tmp, tb, s.v, s.amb, s.pos_a, s.d_count, (int)N, st));
-	ctx->st.esa_launches += 8;
+	ctx->st.esa_launches += 4;
+	ctx->st.cub_calls += 3;
 	u32 m = 0;
 	CK(cudaMemcpyAsync(&m, s.d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
@@ -419,7 +420,8 @@ static int build_suffix_array(andi_ctx *ctx, andi_esa *E) {
 		k_apply_groups<<<nblocks(m, 256), 256, 0, st>>>(s.g, m, s.pos_a, s.vals_b, E->SA, s.grp, s.rank, s.amb);
 		tb = s.tmp_bytes;
 		CK(cub::DeviceSelect::Flagged(s.tmp, tb, s.pos_a, s.amb, s.pos_b, s.d_count, (int)m, st));
-		ctx->st.esa_launches += 7;
+		ctx->st.esa_launches += 3;
+		ctx->st.cub_calls += 3;
 		ctx->st.sa_rounds++;
 		CK(cudaMemcpyAsync(&m, s.d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
@@ -865,8 +867,8 @@ extern "C" int andi_dist_anchor(andi_ctx *ctx, const andi_esa *E, const char *qu
 	return rc;
 }
 
-extern "C" int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
-							  int low_memory, andi_model *out) {
+static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model, int low_memory,
+						  andi_model *out, bool out_on_device) {
 	if (!ctx || !out || s_begin > s_end || s_end > ctx->n) return ANDI_ERR_ARG;
 	if (s_begin == s_end) return ANDI_OK;
 	CK(cudaSetDevice(ctx->device));
@@ -925,9 +927,9 @@ extern "C" int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, doubl
 		}
 		if (!rc) {
 			CK(cudaMemcpyAsync(out + (b0 - s_begin) * n, d_out, (b1 - b0) * n * sizeof(andi_model),
-							   cudaMemcpyDeviceToHost, ctx->stream));
+							   out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
 			CK(cudaStreamSynchronize(ctx->stream));
-			ctx->st.d2h_bytes += (b1 - b0) * n * sizeof(andi_model);
+			if (!out_on_device) ctx->st.d2h_bytes += (b1 - b0) * n * sizeof(andi_model);
 		}
 		for (auto E : live) {
 			esa_release(E);
@@ -939,4 +941,14 @@ extern "C" int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, doubl
 	harvest_events(ctx);
 	dfree(ctx, d_S), dfree(ctx, d_out), dfree(ctx, d_counter);
 	return rc;
+}
+
+extern "C" int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
+							  int low_memory, andi_model *out) {
+	return dist_rows_impl(ctx, s_begin, s_end, p_value, model, low_memory, out, false);
+}
+
+extern "C" int andi_dist_rows_device(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
+									 int low_memory, andi_model *d_out) {
+	return dist_rows_impl(ctx, s_begin, s_end, p_value, model, low_memory, d_out, true);
 }

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "andi_ctx_create", "andi_ctx_destroy", "andi_last_error", "andi_pool_set_host", "andi_pool_set_device",
     "andi_pool_size", "andi_pool_info", "andi_threshold", "andi_esa_build", "andi_esa_build_rs", "andi_esa_free",
     "andi_esa_len", "andi_esa_download", "andi_esa_get_match", "andi_dist_row", "andi_dist_anchor",
-    "andi_dist_rows", "andi_get_stats", "andi_reset_stats",
+    "andi_dist_rows", "andi_dist_rows_device", "andi_get_stats", "andi_reset_stats",
 ]
 
 
@@ -42,7 +42,7 @@ class LcpInter(C.Structure):
 class Stats(C.Structure):
     _fields_ = [
         ("esa_ms", C.c_double), ("walk_ms", C.c_double), ("total_ms", C.c_double),
-        ("esa_launches", C.c_uint64), ("walk_launches", C.c_uint64), ("pairs", C.c_uint64),
+        ("esa_launches", C.c_uint64), ("cub_calls", C.c_uint64), ("walk_launches", C.c_uint64), ("pairs", C.c_uint64),
         ("subjects", C.c_uint64), ("sa_rounds", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
     ]
 
@@ -88,6 +88,7 @@ def load() -> C.CDLL:
     L.andi_dist_row.argtypes = [vp, vp, C.POINTER(sz), sz, sz, C.c_int, C.POINTER(Model)]
     L.andi_dist_anchor.argtypes = [vp, vp, C.c_char_p, sz, sz, C.c_int, C.POINTER(Model)]
     L.andi_dist_rows.argtypes = [vp, sz, sz, C.c_double, C.c_int, C.c_int, vp]
+    L.andi_dist_rows_device.argtypes = [vp, sz, sz, C.c_double, C.c_int, C.c_int, vp]
     L.andi_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.andi_reset_stats.argtypes = [vp]
     L.andi_reset_stats.restype = None
@@ -208,6 +209,12 @@ class Context:
         self._ck(load().andi_dist_rows(self.h, s_begin, s_end, p_value, MODELS[model], int(low_memory),
                                        C.c_void_p(out.ctypes.data)))
         return out
+
+    def dist_rows_device(self, dev_ptr: int, s_begin: int, s_end: int, p_value: float = 0.025, model: str = "JC",
+                         low_memory: bool = False):
+        """Rows [s_begin, s_end) written to device memory at dev_ptr ((s_end-s_begin) * n * 68 bytes)."""
+        self._ck(load().andi_dist_rows_device(self.h, s_begin, s_end, p_value, MODELS[model], int(low_memory),
+                                              C.c_void_p(dev_ptr)))
 
     def stats(self) -> dict:
         s = Stats()

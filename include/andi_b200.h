@@ -117,6 +117,10 @@ int andi_dist_anchor(andi_ctx *ctx, const andi_esa *esa, const char *query, size
  * at a time (F_LOW_MEMORY); results are identical either way (test/test_extra.sh:19-22). */
 int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
 				   int low_memory, andi_model *out);
+/* Same, rows left in device memory (d_out is a device pointer): the form the multi-GPU driver
+ * uses before the NCCL gather of row blocks, and the one bench.py times as `value`. */
+int andi_dist_rows_device(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
+						  int low_memory, andi_model *d_out);
 
 /* Device-side timing of the last andi_dist_rows / andi_esa_build call on this context, taken
  * with CUDA events on the context's stream (milliseconds), plus launch counts. */
@@ -124,7 +128,8 @@ typedef struct andi_stats {
 	double esa_ms;		   /* all index-construction kernels */
 	double walk_ms;		   /* anchor-walk kernels only */
 	double total_ms;	   /* first launch to last completion */
-	uint64_t esa_launches; /* kernels launched for index construction */
+	uint64_t esa_launches; /* OUR kernels launched for index construction (CUB calls not counted) */
+	uint64_t cub_calls;	   /* cub::DeviceRadixSort / DeviceScan / DeviceSelect calls */
 	uint64_t walk_launches;
 	uint64_t pairs;		/* ordered (subject, query) pairs walked */
 	uint64_t subjects;	/* indexes built */
