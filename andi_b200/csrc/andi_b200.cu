@@ -757,198 +757,5 @@ extern "C" int andi_esa_get_match(const andi_esa *E, const char *const *queries,
 	return ANDI_OK;
 }
 
-// ------------------------------------------------------------------ the walk
-
-typedef void (*walk_fn)(const SubjectIndex *, u32, const QueryView *, const u32 *, u32, u32, u32 *,
-						unsigned long long *);
-
-static walk_fn pick_walk(int model, bool spec) {
-	bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
-	if (quarter) return spec ? k_walk<true, true> : k_walk<true, false>;
-	return spec ? k_walk<false, true> : k_walk<false, false>;
-}
-
-// Launch the walk for `nslots` subject indexes against nq queries; d_out gets nslots*nq cells.
-static int launch_walk(andi_ctx *ctx, const SubjectIndex *d_subjects, u32 nslots, const QueryView *d_queries,
-					   const u32 *d_query_ids, u32 nq, u32 threshold_override, int model, bool spec, u32 *d_out,
-					   unsigned long long *d_counter) {
-	walk_fn fn = pick_walk(model, spec);
-	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
-	if (per_sm < 1) per_sm = 1;
-	unsigned long long total = (unsigned long long)nslots * nq;
-	unsigned grid = (unsigned)std::min<unsigned long long>((total + 255) / 256,
-															(unsigned long long)per_sm * ctx->sm_count);
-	CK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), ctx->stream));
-	cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
-	mark(ctx, e0);
-	if (!ctx->first_ev) {
-		ctx->first_ev = get_event(ctx);
-		mark(ctx, ctx->first_ev);
-	}
-	fn<<<grid, 256, 0, ctx->stream>>>(d_subjects, nslots, d_queries, d_query_ids, nq, threshold_override, d_out,
-									   d_counter);
-	mark(ctx, e1);
-	ctx->walk_ev.emplace_back(e0, e1);
-	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);
-	mark(ctx, ctx->last_ev);
-	ctx->st.walk_launches++;
-	ctx->st.pairs += total;
-	CK(cudaGetLastError());
-	return ANDI_OK;
-}
-
-extern "C" int andi_dist_row(andi_ctx *ctx, const andi_esa *E, const size_t *query_ids, size_t nq,
-							 size_t threshold, int model, andi_model *out) {
-	if (!ctx || !E || !query_ids || !out || E->ctx != ctx) return ANDI_ERR_ARG;
-	if (nq == 0) return ANDI_OK;
-	CK(cudaSetDevice(ctx->device));
-	std::vector<u32> ids(nq);
-	bool spec = E->has_sep;
-	for (size_t k = 0; k < nq; k++) {
-		if (query_ids[k] >= ctx->n) return ANDI_ERR_ARG;
-		ids[k] = (u32)query_ids[k];
-		spec |= ctx->has_sep[ids[k]] != 0;
-	}
-	SubjectIndex S = subject_index(E);
-	S.self = 0xffffffffu;  // dist_anchor itself has no notion of "self"
-	if (threshold < (size_t)S.K) S.K = 0;  // directory assumes K <= threshold
-	SubjectIndex *d_S = nullptr;
-	u32 *d_ids = nullptr, *d_out = nullptr;
-	unsigned long long *d_counter = nullptr;
-	CK(dalloc(ctx, &d_S, 1));
-	CK(dalloc(ctx, &d_ids, nq));
-	CK(dalloc(ctx, &d_out, nq * 17));
-	CK(dalloc(ctx, &d_counter, 1));
-	CK(cudaMemcpyAsync(d_S, &S, sizeof S, cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaMemcpyAsync(d_ids, ids.data(), nq * 4, cudaMemcpyHostToDevice, ctx->stream));
-	int rc = launch_walk(ctx, d_S, 1, ctx->d_queries, d_ids, (u32)nq, (u32)threshold, model, spec, d_out, d_counter);
-	if (!rc) {
-		CK(cudaMemcpyAsync(out, d_out, nq * sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaStreamSynchronize(ctx->stream));
-		ctx->st.d2h_bytes += nq * sizeof(andi_model);
-		harvest_events(ctx);
-	}
-	dfree(ctx, d_S), dfree(ctx, d_ids), dfree(ctx, d_out), dfree(ctx, d_counter);
-	return rc;
-}
-
-extern "C" int andi_dist_anchor(andi_ctx *ctx, const andi_esa *E, const char *query, size_t qlen,
-								size_t threshold, int model, andi_model *out) {
-	if (!ctx || !E || !query || !out || E->ctx != ctx) return ANDI_ERR_ARG;
-	CK(cudaSetDevice(ctx->device));
-	if (qlen == 0) {
-		memset(out, 0, sizeof *out);
-		return ANDI_OK;
-	}
-	TempQueries T;
-	int rc = temp_queries(ctx, &query, &qlen, 1, T);
-	if (rc) return rc;
-	SubjectIndex S = subject_index(E);
-	S.self = 0xffffffffu;
-	if (threshold < (size_t)S.K) S.K = 0;
-	SubjectIndex *d_S = nullptr;
-	u32 *d_out = nullptr;
-	unsigned long long *d_counter = nullptr;
-	CK(dalloc(ctx, &d_S, 1));
-	CK(dalloc(ctx, &d_out, 17));
-	CK(dalloc(ctx, &d_counter, 1));
-	CK(cudaMemcpyAsync(d_S, &S, sizeof S, cudaMemcpyHostToDevice, ctx->stream));
-	rc = launch_walk(ctx, d_S, 1, T.d_views, nullptr, 1, (u32)threshold, model, E->has_sep || T.any_sep, d_out,
-					 d_counter);
-	if (!rc) {
-		CK(cudaMemcpyAsync(out, d_out, sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaStreamSynchronize(ctx->stream));
-		ctx->st.d2h_bytes += sizeof(andi_model);
-		harvest_events(ctx);
-	}
-	dfree(ctx, d_S), dfree(ctx, d_out), dfree(ctx, d_counter);
-	temp_release(ctx, T);
-	return rc;
-}
-
-static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model, int low_memory,
-						  andi_model *out, bool out_on_device) {
-	if (!ctx || !out || s_begin > s_end || s_end > ctx->n) return ANDI_ERR_ARG;
-	if (s_begin == s_end) return ANDI_OK;
-	CK(cudaSetDevice(ctx->device));
-	const size_t n = ctx->n;
-	// Subjects per walk launch: enough pairs in flight to fill the GPU (one thread per pair),
-	// bounded by a memory budget for resident indexes; 1 in low-memory mode.
-	size_t free_b = 0, total_b = 0;
-	cudaMemGetInfo(&free_b, &total_b);
-	size_t maxlen = 0;
-	for (size_t i = s_begin; i < s_end; i++) maxlen = std::max(maxlen, ctx->len[i]);
-	size_t per_index = (2 * maxlen + 2) * 9 + ((size_t)4 << 24) + (64u << 20);
-	size_t want_pairs = (size_t)ctx->sm_count * 2048;
-	size_t batch = low_memory ? 1 : std::max<size_t>(1, (want_pairs + n - 1) / n);
-	batch = std::min(batch, std::max<size_t>(1, (free_b / 2) / per_index));
-	batch = std::min(batch, s_end - s_begin);
-
-	SubjectIndex *d_S = nullptr;
-	u32 *d_out = nullptr;
-	unsigned long long *d_counter = nullptr;
-	CK(dalloc(ctx, &d_S, batch));
-	CK(dalloc(ctx, &d_out, batch * n * 17));
-	CK(dalloc(ctx, &d_counter, 1));
-	std::vector<SubjectIndex> hS(batch);
-	std::vector<andi_esa *> live;
-	int rc = ANDI_OK;
-	for (size_t b0 = s_begin; b0 < s_end && !rc; b0 += batch) {
-		size_t b1 = std::min(b0 + batch, s_end);
-		bool spec = ctx->any_sep;
-		for (size_t i = b0; i < b1 && !rc; i++) {
-			andi_esa *E = new andi_esa();
-			E->ctx = ctx;
-			E->n = (u32)ctx->len[i];
-			E->N = 2 * E->n + 1;
-			E->has_sep = ctx->has_sep[i] != 0;
-			E->self = (u32)i;
-			E->threshold = (u32)andi_threshold(p_value, ctx->gc[i], E->N);
-			E->K = choose_depth(E->N, E->threshold);
-			size_t nw = plane_words(E->N);
-			live.push_back(E);
-			if (dalloc(ctx, &E->code, nw) != cudaSuccess || dalloc(ctx, &E->spec, nw) != cudaSuccess) {
-				ctx->err = "device allocation failed";
-				rc = ANDI_ERR_NOMEM;
-				break;
-			}
-			k_build_rs<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(ctx->pool_code + ctx->word_off[i],
-																   ctx->pool_spec + ctx->word_off[i], E->n, E->code,
-																   E->spec, (u32)nw);
-			ctx->st.esa_launches++;
-			rc = build_index(ctx, E, ANDI_ESA_SEARCH);
-			hS[i - b0] = subject_index(E);
-		}
-		if (!rc) {
-			CK(cudaMemcpyAsync(d_S, hS.data(), (b1 - b0) * sizeof(SubjectIndex), cudaMemcpyHostToDevice, ctx->stream));
-			rc = launch_walk(ctx, d_S, (u32)(b1 - b0), ctx->d_queries, nullptr, (u32)n, 0, model, spec, d_out,
-							 d_counter);
-		}
-		if (!rc) {
-			CK(cudaMemcpyAsync(out + (b0 - s_begin) * n, d_out, (b1 - b0) * n * sizeof(andi_model),
-							   out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaStreamSynchronize(ctx->stream));
-			if (!out_on_device) ctx->st.d2h_bytes += (b1 - b0) * n * sizeof(andi_model);
-		}
-		for (auto E : live) {
-			esa_release(E);
-			delete E;
-		}
-		live.clear();
-	}
-	cudaStreamSynchronize(ctx->stream);
-	harvest_events(ctx);
-	dfree(ctx, d_S), dfree(ctx, d_out), dfree(ctx, d_counter);
-	return rc;
-}
-
-extern "C" int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
-							  int low_memory, andi_model *out) {
-	return dist_rows_impl(ctx, s_begin, s_end, p_value, model, low_memory, out, false);
-}
-
-extern "C" int andi_dist_rows_device(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
-									 int low_memory, andi_model *d_out) {
-	return dist_rows_impl(ctx, s_begin, s_end, p_value, model, low_memory, d_out, true);
-}
+// ------------------------------------------------------------------ the walk (host side)
+#include "walk_host.cuh"

@@ -1,0 +1,213 @@
+// andi_b200/csrc/walk_host.cuh -- host side of the anchor walk; included by andi_b200.cu.
+//
+// distMatrix / distMatrixLM (src/dist_hack.h:34-96): for every subject build its index, walk
+// every query against it. One subject is resident at a time (its index lives in L2 while the
+// queries stream), which is also what F_LOW_MEMORY asks for; the parallelism comes from
+// splitting every query into chunks (walk_kernels.cuh).
+#pragma once
+
+typedef void (*chunks_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, u32 *);
+typedef void (*reduce_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, const u32 *, u32 *);
+
+static void pick_walk(int model, bool spec, chunks_fn &cf, reduce_fn &rf) {
+	bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
+	if (quarter && spec) cf = k_walk_chunks<true, true>, rf = k_walk_reduce<true, true>;
+	if (quarter && !spec) cf = k_walk_chunks<true, false>, rf = k_walk_reduce<true, false>;
+	if (!quarter && spec) cf = k_walk_chunks<false, true>, rf = k_walk_reduce<false, true>;
+	if (!quarter && !spec) cf = k_walk_chunks<false, false>, rf = k_walk_reduce<false, false>;
+}
+
+// Chunk length: aim at ~8 units per resident thread so the grid-stride loop balances, keep
+// chunks long enough that the boundary replay (a handful of steps) stays a small fraction.
+static u32 pick_chunk(const andi_ctx *ctx, unsigned long long total_bases) {
+	unsigned long long target_units = (unsigned long long)ctx->sm_count * 1024ULL * 8ULL;
+	unsigned long long want = total_bases / target_units;
+	u32 chunk = 1024;
+	while (chunk < want && chunk < 16384) chunk *= 2;
+	const char *env = getenv("ANDI_B200_CHUNK");
+	if (env && atoi(env) >= 64) chunk = (u32)atoi(env);
+	return chunk;
+}
+
+struct WalkPlan {
+	u32 chunk = 0, cpq = 0;
+	size_t record_words = 0;
+};
+
+static WalkPlan plan_walk(const andi_ctx *ctx, const std::vector<size_t> &qlens) {
+	WalkPlan p;
+	unsigned long long total = 0;
+	size_t maxlen = 0;
+	for (size_t l : qlens) total += l, maxlen = std::max(maxlen, l);
+	p.chunk = pick_chunk(ctx, total);
+	p.cpq = (u32)((maxlen + p.chunk - 1) / p.chunk);
+	if (p.cpq == 0) p.cpq = 1;
+	p.record_words = qlens.size() * (size_t)p.cpq * ANDI_UNIT_WORDS;
+	return p;
+}
+
+// Walk nq queries against one index; d_out gets nq cells of 17 words.
+static int launch_walk(andi_ctx *ctx, const SubjectIndex &S, const QueryView *d_queries, const u32 *d_query_ids,
+					   u32 nq, const WalkPlan &plan, u32 threshold, int model, bool spec, u32 *d_records,
+					   u32 *d_out) {
+	chunks_fn cf = nullptr;
+	reduce_fn rf = nullptr;
+	pick_walk(model, spec, cf, rf);
+	int per_sm = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf, ANDI_WALK_THREADS, 0));
+	if (per_sm < 1) per_sm = 1;
+	unsigned long long units = (unsigned long long)nq * plan.cpq;
+	unsigned grid = (unsigned)std::min<unsigned long long>((units + ANDI_WALK_THREADS - 1) / ANDI_WALK_THREADS,
+															(unsigned long long)per_sm * ctx->sm_count);
+	cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+	mark(ctx, e0);
+	if (!ctx->first_ev) {
+		ctx->first_ev = get_event(ctx);
+		mark(ctx, ctx->first_ev);
+	}
+	cf<<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
+													 d_records);
+	rf<<<nblocks(nq, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
+												   d_records, d_out);
+	mark(ctx, e1);
+	ctx->walk_ev.emplace_back(e0, e1);
+	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);
+	mark(ctx, ctx->last_ev);
+	ctx->st.walk_launches += 2;
+	ctx->st.pairs += nq;
+	CK(cudaGetLastError());
+	return ANDI_OK;
+}
+
+extern "C" int andi_dist_row(andi_ctx *ctx, const andi_esa *E, const size_t *query_ids, size_t nq,
+							 size_t threshold, int model, andi_model *out) {
+	if (!ctx || !E || !query_ids || !out || E->ctx != ctx) return ANDI_ERR_ARG;
+	if (nq == 0) return ANDI_OK;
+	CK(cudaSetDevice(ctx->device));
+	std::vector<u32> ids(nq);
+	std::vector<size_t> qlens(nq);
+	bool spec = E->has_sep;
+	for (size_t k = 0; k < nq; k++) {
+		if (query_ids[k] >= ctx->n) return ANDI_ERR_ARG;
+		ids[k] = (u32)query_ids[k];
+		qlens[k] = ctx->len[ids[k]];
+		spec |= ctx->has_sep[ids[k]] != 0;
+	}
+	SubjectIndex S = subject_index(E);
+	S.self = 0xffffffffu;				   // dist_anchor itself has no notion of "self"
+	if (threshold < (size_t)S.K) S.K = 0;  // the directory assumes K <= threshold
+	WalkPlan plan = plan_walk(ctx, qlens);
+	u32 *d_ids = nullptr, *d_out = nullptr, *d_rec = nullptr;
+	CK(dalloc(ctx, &d_ids, nq));
+	CK(dalloc(ctx, &d_out, nq * 17));
+	CK(dalloc(ctx, &d_rec, plan.record_words));
+	CK(cudaMemcpyAsync(d_ids, ids.data(), nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+	int rc = launch_walk(ctx, S, ctx->d_queries, d_ids, (u32)nq, plan, (u32)threshold, model, spec, d_rec, d_out);
+	if (!rc) {
+		CK(cudaMemcpyAsync(out, d_out, nq * sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		ctx->st.d2h_bytes += nq * sizeof(andi_model);
+		harvest_events(ctx);
+	}
+	dfree(ctx, d_ids), dfree(ctx, d_out), dfree(ctx, d_rec);
+	return rc;
+}
+
+extern "C" int andi_dist_anchor(andi_ctx *ctx, const andi_esa *E, const char *query, size_t qlen,
+								size_t threshold, int model, andi_model *out) {
+	if (!ctx || !E || !query || !out || E->ctx != ctx) return ANDI_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	if (qlen == 0) {
+		memset(out, 0, sizeof *out);
+		return ANDI_OK;
+	}
+	if (qlen > (size_t)INT_MAX) return ANDI_ERR_TOO_LONG;
+	TempQueries T;
+	int rc = temp_queries(ctx, &query, &qlen, 1, T);
+	if (rc) return rc;
+	SubjectIndex S = subject_index(E);
+	S.self = 0xffffffffu;
+	if (threshold < (size_t)S.K) S.K = 0;
+	WalkPlan plan = plan_walk(ctx, std::vector<size_t>{qlen});
+	u32 *d_out = nullptr, *d_rec = nullptr;
+	CK(dalloc(ctx, &d_out, 17));
+	CK(dalloc(ctx, &d_rec, plan.record_words));
+	rc = launch_walk(ctx, S, T.d_views, nullptr, 1, plan, (u32)threshold, model, E->has_sep || T.any_sep, d_rec, d_out);
+	if (!rc) {
+		CK(cudaMemcpyAsync(out, d_out, sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		ctx->st.d2h_bytes += sizeof(andi_model);
+		harvest_events(ctx);
+	}
+	dfree(ctx, d_out), dfree(ctx, d_rec);
+	temp_release(ctx, T);
+	return rc;
+}
+
+static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model, int low_memory,
+						  andi_model *out, bool out_on_device) {
+	(void)low_memory;  // one index is resident at a time in either mode (src/dist_hack.h:14-16)
+	if (!ctx || !out || s_begin > s_end || s_end > ctx->n) return ANDI_ERR_ARG;
+	if (s_begin == s_end) return ANDI_OK;
+	CK(cudaSetDevice(ctx->device));
+	const size_t n = ctx->n, rows = s_end - s_begin;
+	WalkPlan plan = plan_walk(ctx, ctx->len);
+	u32 *d_rec = nullptr, *d_out = nullptr;
+	CK(dalloc(ctx, &d_rec, plan.record_words));
+	if (out_on_device)
+		d_out = (u32 *)out;
+	else
+		CK(dalloc(ctx, &d_out, rows * n * 17));
+	int rc = ANDI_OK;
+	for (size_t i = s_begin; i < s_end && !rc; i++) {
+		andi_esa E;
+		E.ctx = ctx;
+		E.n = (u32)ctx->len[i];
+		E.N = 2 * E.n + 1;
+		E.has_sep = ctx->has_sep[i] != 0;
+		E.self = (u32)i;
+		E.threshold = (u32)andi_threshold(p_value, ctx->gc[i], E.N);
+		E.K = choose_depth(E.N, E.threshold);
+		size_t nw = plane_words(E.N);
+		if (dalloc(ctx, &E.code, nw) != cudaSuccess || dalloc(ctx, &E.spec, nw) != cudaSuccess) {
+			ctx->err = "device allocation failed";
+			rc = ANDI_ERR_NOMEM;
+		}
+		if (!rc) {
+			k_build_rs<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(ctx->pool_code + ctx->word_off[i],
+																   ctx->pool_spec + ctx->word_off[i], E.n, E.code,
+																   E.spec, (u32)nw);
+			ctx->st.esa_launches++;
+			rc = build_index(ctx, &E, ANDI_ESA_SEARCH);
+		}
+		if (!rc) {
+			SubjectIndex S = subject_index(&E);
+			rc = launch_walk(ctx, S, ctx->d_queries, nullptr, (u32)n, plan, E.threshold, model,
+							 ctx->any_sep || E.has_sep, d_rec, d_out + (i - s_begin) * n * 17);
+		}
+		esa_release(&E);
+	}
+	if (!rc && !out_on_device) {
+		CK(cudaMemcpyAsync(out, d_out, rows * n * sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->st.d2h_bytes += rows * n * sizeof(andi_model);
+	}
+	cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	if (!rc && e != cudaSuccess) {
+		ctx->err = std::string("walk: ") + cudaGetErrorString(e);
+		rc = ANDI_ERR_CUDA;
+	}
+	harvest_events(ctx);
+	dfree(ctx, d_rec);
+	if (!out_on_device) dfree(ctx, d_out);
+	return rc;
+}
+
+extern "C" int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
+							  int low_memory, andi_model *out) {
+	return dist_rows_impl(ctx, s_begin, s_end, p_value, model, low_memory, out, false);
+}
+
+extern "C" int andi_dist_rows_device(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
+									 int low_memory, andi_model *d_out) {
+	return dist_rows_impl(ctx, s_begin, s_end, p_value, model, low_memory, d_out, true);
+}

@@ -1,15 +1,30 @@
 // andi_b200/csrc/walk_kernels.cuh -- the anchor walk.
 //
-// One thread owns one ordered (subject, query) pair and runs the reference's state machine
-// (src/process.c:141-214) exactly: lucky anchor on the previous diagonal first
-// (process.c:82-100), otherwise a longest-match lookup in the subject index
-// (process.c:113-123), then the right-anchor pairing and the one-anchor-late accounting
-// (process.c:160-211). All text is 2-bit packed; comparisons are XOR + find-first-set on
-// 32-character windows, gap columns are classified with popcounts.
+// The reference walks a query sequentially (src/process.c:141-214); the state that carries
+// from one loop iteration to the next is exactly
+//     (pos_Q, last_match.{pos_S,pos_Q,length}, last_was_right_anchor)             [WalkState]
+// plus the running counts. Two walks that reach the same WalkState behave identically from
+// there on. That gives the parallel form used here (exact, not an approximation):
+//
+//   k_walk_chunks  one thread per (query, chunk). It walks its chunk from an "amnesic" state
+//                  (no previous anchor) -> counts U_c and exit state E_c. Then it plays the
+//                  TRUE successor: it continues from E_c into chunk c+1 while also replaying
+//                  the amnesic walk of chunk c+1, one step at a time, until both chains are in
+//                  the same WalkState. The counts of the true chain minus those of the amnesic
+//                  chain up to that point are the boundary correction D_c.
+//   k_walk_reduce  one thread per pair: total = sum_c (U_c + D_c) while every boundary
+//                  synchronised; where one did not (e.g. a long anchor-free stretch) it walks on
+//                  sequentially from the last known true state until the chains meet again.
+//
+// All threads of a launch work on ONE subject, so its index (SA, directory, packed text) stays
+// resident in the 126 MB L2 while the queries stream through. The main loop has a single back
+// edge with a __syncwarp so the 32 walks of a warp stay converged step by step.
 #pragma once
 #include "esa_kernels.cuh"
 
 #define ANDI_SCAN_MAX 8
+#define ANDI_WALK_THREADS 256
+#define ANDI_UNIT_WORDS 38	// U[16] D[16] E[5] flag
 
 struct SubjectIndex {
 	TextView rs;		   // RS planes, len = N = 2n+1, mid = n
@@ -85,7 +100,8 @@ __device__ MatchResult search_range(const SubjectIndex &S, const TextView &q, u3
 // when the k-mer is absent only the LENGTH of the match matters (it is < K <= threshold, so
 // no anchor can result) and the presence bitmaps give it without touching the suffix array.
 template <bool SPEC>
-__device__ MatchResult longest_match(const SubjectIndex &S, const TextView &q, u32 qpos, u32 rem) {
+__device__ __forceinline__ MatchResult longest_match(const SubjectIndex &S, const TextView &q, u32 qpos,
+													 u32 rem) {
 	const int K = S.K;
 	bool direct = K > 0 && rem >= (u32)K;
 	u64 cw = 0;
@@ -130,24 +146,33 @@ __device__ MatchResult longest_match(const SubjectIndex &S, const TextView &q, u
 	return r;
 }
 
-// ---- counting (src/model.c)
-struct Counts {
+// ---- count accumulators. add(cell, v) adds to one of the 16 cells of src/model.h:14-32.
+// Shared-memory flavour: one column of a [16][threads] array per thread (conflict free,
+// dynamically indexable without local memory); `sign` is +1 or -1 (as u32) so the amnesic
+// chain of a boundary replay can be subtracted in place.
+struct SharedAcc {
+	u32 *col;  // &cells[0][threadIdx.x]
+	u32 sign;
+	__device__ __forceinline__ void add(u32 cell, u32 v) { col[cell * ANDI_WALK_THREADS] += v * sign; }
+};
+struct LocalAcc {
 	u32 c[16];
+	__device__ __forceinline__ void add(u32 cell, u32 v) { c[cell] += v; }
 };
 
 // src/model.c:309-337: classify `len` aligned columns; columns with a separator on either
 // side are skipped. 32 columns per step: four "subject is base a" masks, four "query is
 // base b" masks, sixteen popcounts.
-template <bool SPEC>
-__device__ __forceinline__ void count_columns(Counts &M, const TextView &s, u32 ps, const TextView &q,
-											  u32 pq, u32 len) {
+template <bool SPEC, class Acc>
+__device__ __forceinline__ void count_columns(Acc &M, const TextView &s, u32 ps, const TextView &q, u32 pq,
+											  u32 len) {
 	for (u32 k = 0; k < len; k += 32) {
 		u32 span = min(32u, len - k);
 		u64 valid = span == 32 ? ANDI_EVEN_BITS : (ANDI_EVEN_BITS & ((1ULL << (2 * span)) - 1ULL));
 		u64 sw = window32(s.code, ps + k), qw = window32(q.code, pq + k);
 		if (SPEC) valid &= ~(window32(s.spec, ps + k) | window32(q.spec, pq + k));
 		if (span == 1) {  // by far the most common gap: a single substitution
-			if (valid) M.c[((u32)sw & 3u) * 4u + ((u32)qw & 3u)]++;
+			if (valid) M.add(((u32)sw & 3u) * 4u + ((u32)qw & 3u), 1);
 			continue;
 		}
 		u64 s_lo = sw & ANDI_EVEN_BITS, s_hi = (sw >> 1) & ANDI_EVEN_BITS;
@@ -157,116 +182,281 @@ __device__ __forceinline__ void count_columns(Counts &M, const TextView &s, u32 
 #pragma unroll
 		for (int a = 0; a < 4; a++)
 #pragma unroll
-			for (int b = 0; b < 4; b++) M.c[a * 4 + b] += __popcll(sm[a] & qm[b] & valid);
+			for (int b = 0; b < 4; b++) {
+				u32 n = __popcll(sm[a] & qm[b] & valid);
+				if (n) M.add(a * 4 + b, n);
+			}
 	}
 }
 
 // src/model.c:246-279. QUARTER (RAW/JC/KIMURA): len/4 to each diagonal cell, remainder to
 // TtoT, no text is read. Otherwise (LOGDET/ANI) the composition of the query slice, separators
 // skipped.
-template <bool QUARTER, bool SPEC>
-__device__ __forceinline__ void count_anchor(Counts &M, const TextView &q, u32 pq, u32 len) {
+template <bool QUARTER, bool SPEC, class Acc>
+__device__ __forceinline__ void count_anchor(Acc &M, const TextView &q, u32 pq, u32 len) {
 	if (QUARTER) {
 		u32 f = len >> 2;
-		M.c[0] += f, M.c[5] += f, M.c[10] += f, M.c[15] += f + (len & 3u);
+		M.add(0, f), M.add(5, f), M.add(10, f), M.add(15, f + (len & 3u));
 		return;
 	}
+	u32 a = 0, c = 0, g = 0, t = 0;
 	for (u32 k = 0; k < len; k += 32) {
 		u32 span = min(32u, len - k);
 		u64 valid = span == 32 ? ANDI_EVEN_BITS : (ANDI_EVEN_BITS & ((1ULL << (2 * span)) - 1ULL));
 		u64 qw = window32(q.code, pq + k);
 		if (SPEC) valid &= ~window32(q.spec, pq + k);
 		u64 lo = qw & ANDI_EVEN_BITS, hi = (qw >> 1) & ANDI_EVEN_BITS;
-		M.c[0] += __popcll(~hi & ~lo & valid);
-		M.c[5] += __popcll(~hi & lo & valid);
-		M.c[10] += __popcll(hi & ~lo & valid);
-		M.c[15] += __popcll(hi & lo & valid);
+		a += __popcll(~hi & ~lo & valid);
+		c += __popcll(~hi & lo & valid);
+		g += __popcll(hi & ~lo & valid);
+		t += __popcll(hi & lo & valid);
+	}
+	M.add(0, a), M.add(5, c), M.add(10, g), M.add(15, t);
+}
+
+// ---- the state that carries across iterations of the loop at src/process.c:153-197
+struct WalkState {
+	u32 pos_q;						 // this_match.pos_Q
+	u32 last_s, last_q, last_len;	 // last_match
+	u32 paired;						 // last_was_right_anchor
+};
+
+__device__ __forceinline__ bool same_state(const WalkState &a, const WalkState &b) {
+	return a.pos_q == b.pos_q && a.last_s == b.last_s && a.last_q == b.last_q && a.last_len == b.last_len &&
+		   a.paired == b.paired;
+}
+
+__device__ __forceinline__ WalkState amnesic_state(u32 pos) {
+	WalkState w;
+	w.pos_q = pos, w.last_s = 0, w.last_q = 0, w.last_len = 0, w.paired = 0;
+	return w;
+}
+
+// One iteration of the loop at src/process.c:153-197.
+template <bool QUARTER, bool SPEC, class Acc>
+__device__ __forceinline__ void walk_step(const SubjectIndex &S, const TextView &q, u32 t, WalkState &w,
+										  Acc &M) {
+	const u32 qlen = q.len, N = S.rs.len, border = N / 2;
+	const u32 pos_q = w.pos_q, rem = qlen - pos_q;
+	u32 cur_s = 0, cur_len = 0;
+	bool found = false;
+	// process.c:86-99: same diagonal as the previous anchor, no uniqueness test
+	u32 advance = pos_q - w.last_q;
+	u32 gap = advance - w.last_len;
+	u32 guess = w.last_s + advance;
+	if (guess < N && gap <= t) {
+		cur_s = guess;
+		cur_len = match_len<SPEC>(q, pos_q, S.rs, guess, min(rem, rs_run<SPEC>(S.rs, guess)));
+		found = cur_len >= t;
+	}
+	if (!found) {
+		// process.c:117-122
+		MatchResult m = longest_match<SPEC>(S, q, pos_q, rem);
+		cur_len = m.len;
+		found = m.unique && m.len >= t;
+		if (found) cur_s = __ldg(S.SA + m.at);
+	}
+	if (found) {
+		// process.c:160-193
+		u32 end_s = w.last_s + w.last_len, end_q = w.last_q + w.last_len;
+		bool pairs = cur_s > end_s && (pos_q - end_q) == (cur_s - end_s) && ((cur_s < border) == (w.last_s < border));
+		if (pairs) {
+			count_anchor<QUARTER, SPEC>(M, q, w.last_q, w.last_len);
+			count_columns<SPEC>(M, S.rs, end_s, q, end_q, pos_q - end_q);
+			w.paired = 1;
+		} else {
+			if (w.paired || w.last_len >= 2 * t) count_anchor<QUARTER, SPEC>(M, q, w.last_q, w.last_len);
+			w.paired = 0;
+		}
+		w.last_s = cur_s, w.last_q = pos_q, w.last_len = cur_len;
+	}
+	w.pos_q = pos_q + cur_len + 1;	// process.c:196
+}
+
+// src/process.c:199-211: what is still owed once the loop has ended in state w.
+template <bool QUARTER, bool SPEC, class Acc>
+__device__ __forceinline__ void walk_tail(const TextView &q, u32 t, const WalkState &w, Acc &M) {
+	if (w.last_len >= q.len) {
+		count_anchor<QUARTER, SPEC>(M, q, 0, q.len);
+	} else if (w.paired || w.last_len >= 2 * t) {
+		count_anchor<QUARTER, SPEC>(M, q, w.last_q, w.last_len);
 	}
 }
 
-// ---- src/process.c:141-214 for one pair
+// ---- k_walk_chunks: see the header of this file. Record layout per unit (ANDI_UNIT_WORDS):
+// [0,16) U_c   counts of the amnesic walk of chunk c
+// [16,32) D_c  (true chain - amnesic chain) of chunk c+1 up to their meeting point
+// [32,37) E_c  exit state of the amnesic walk of chunk c
+// [37]    1 if the boundary into chunk c+1 synchronised (or c is the last chunk), else 0
 template <bool QUARTER, bool SPEC>
-__device__ void walk_pair(const SubjectIndex &S, const TextView &q, u32 threshold, u32 *out17) {
-	Counts M;
-#pragma unroll
-	for (int k = 0; k < 16; k++) M.c[k] = 0;
-	const u32 qlen = q.len, N = S.rs.len, border = N / 2, t = threshold;
-	u32 pos_q = 0;							 // this_match.pos_Q
-	u32 cur_s = 0, cur_len = 0;				 // this_match.pos_S, .length
-	u32 last_s = 0, last_q = 0, last_len = 0; // last_match
-	bool last_paired = false;				 // last_was_right_anchor
+__global__ void __launch_bounds__(ANDI_WALK_THREADS)
+k_walk_chunks(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
+			  u32 nq, u32 chunk, u32 cpq, u32 threshold, u32 *__restrict__ records) {
+	__shared__ u32 cells[2][16][ANDI_WALK_THREADS];
+	const u32 tid = threadIdx.x;
+	const unsigned long long total = (unsigned long long)nq * cpq;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	unsigned long long unit = (unsigned long long)blockIdx.x * blockDim.x + tid;
+	const u32 t = threshold;
 
-	while (pos_q < qlen) {
-		const u32 rem = qlen - pos_q;
-		bool found = false;
-		// process.c:86-99: same diagonal as the previous anchor, no uniqueness test
-		u32 advance = pos_q - last_q;
-		u32 gap = advance - last_len;
-		u32 guess = last_s + advance;
-		if (guess < N && gap <= t) {
-			cur_s = guess;
-			cur_len = match_len<SPEC>(q, pos_q, S.rs, guess, min(rem, rs_run<SPEC>(S.rs, guess)));
-			found = cur_len >= t;
-		}
-		if (!found) {
-			// process.c:117-122
-			MatchResult m = longest_match<SPEC>(S, q, pos_q, rem);
-			cur_len = m.len;
-			found = m.unique && m.len >= t;
-			if (found) cur_s = __ldg(S.SA + m.at);
-		}
-		if (found) {
-			u32 end_s = last_s + last_len, end_q = last_q + last_len;
-			bool pairs = cur_s > end_s && (pos_q - end_q) == (cur_s - end_s) &&
-						 ((cur_s < border) == (last_s < border));
-			if (pairs) {
-				count_anchor<QUARTER, SPEC>(M, q, last_q, last_len);
-				count_columns<SPEC>(M, S.rs, end_s, q, end_q, pos_q - end_q);
-				last_paired = true;
-			} else {
-				if (last_paired || last_len >= 2 * t) count_anchor<QUARTER, SPEC>(M, q, last_q, last_len);
-				last_paired = false;
-			}
-			last_s = cur_s, last_q = pos_q, last_len = cur_len;
-		}
-		pos_q += cur_len + 1;
-	}
-	// process.c:199-211
-	if (last_len >= qlen) {
-		count_anchor<QUARTER, SPEC>(M, q, 0, qlen);
-	} else if (last_paired || last_len >= 2 * t) {
-		count_anchor<QUARTER, SPEC>(M, q, last_q, last_len);
-	}
-#pragma unroll
-	for (int k = 0; k < 16; k++) out17[k] = M.c[k];
-	out17[16] = qlen;
-}
+	bool active = false;
+	int phase = 1;
+	TextView q;
+	q.code = nullptr, q.spec = nullptr, q.len = 0, q.mid = 0xffffffffu;
+	WalkState A = amnesic_state(0), B = amnesic_state(0), E = amnesic_state(0);
+	u32 a_true = 1;			   // phase 2: A is the true chain (B the amnesic one) or the other way round
+	u32 c_end = 0, c2_end = 0;  // end of the own chunk / of the next chunk
 
-// Pair p of a batch: subject slot p / nq, query p % nq. A persistent grid pulls pair ids from
-// a global counter so finished threads pick up new work immediately.
-template <bool QUARTER, bool SPEC>
-__global__ void __launch_bounds__(256)
-k_walk(const SubjectIndex *__restrict__ subjects, u32 nslots, const QueryView *__restrict__ queries,
-	   const u32 *__restrict__ query_ids, u32 nq, u32 threshold_override, u32 *__restrict__ out,
-	   unsigned long long *__restrict__ next_pair) {
-	const unsigned long long total = (unsigned long long)nslots * nq;
 	for (;;) {
-		unsigned long long p = atomicAdd(next_pair, 1ULL);
-		if (p >= total) return;
-		u32 slot = (u32)(p / nq), k = (u32)(p % nq);
-		u32 qid = query_ids ? query_ids[k] : k;
-		const SubjectIndex &S = subjects[slot];
-		u32 *cell = out + (size_t)p * 17;
-		if (qid == S.self) {
-			// src/dist_hack.h:61-64
-			cell[0] = 9;
-			for (int c = 1; c < 16; c++) cell[c] = 0;
-			cell[16] = 9;
+		if (!active) {
+			while (unit < total) {
+				u32 k = (u32)(unit / cpq), c = (u32)(unit % cpq);
+				u32 qid = query_ids ? query_ids[k] : k;
+				u32 qlen = queries[qid].t.len;
+				unsigned long long cs = (unsigned long long)c * chunk;
+				if (qid != S.self && cs < qlen) {
+					q = queries[qid].t;
+					A = amnesic_state((u32)cs);
+					c_end = (u32)min((unsigned long long)qlen, cs + chunk);
+					c2_end = (u32)min((unsigned long long)qlen, cs + 2ULL * chunk);
+					phase = 1;
+					active = true;
+#pragma unroll
+					for (int x = 0; x < 16; x++) cells[0][x][tid] = 0, cells[1][x][tid] = 0;
+					break;
+				}
+				unit += stride;
+			}
+		}
+		if (!__any_sync(0xffffffffu, active)) break;
+		if (active) {
+			bool finished = false;
+			u32 flag = 1;
+			if (phase == 1) {
+				SharedAcc acc = {&cells[0][0][tid], 1u};
+				walk_step<QUARTER, SPEC>(S, q, t, A, acc);
+				if (A.pos_q >= c_end) {
+					E = A;
+					if (c_end >= q.len) {
+						finished = true;  // last chunk: nothing follows
+					} else {
+						phase = 2;
+						B = amnesic_state(c_end);
+						a_true = 1;
+					}
+				}
+			} else {
+				// A and B are the two chains inside chunk c+1; a_true says which one A is.
+				const WalkState &T = a_true ? A : B;
+				const WalkState &P = a_true ? B : A;
+				if (same_state(A, B)) {
+					finished = true;
+				} else if (T.pos_q >= c2_end || P.pos_q >= c2_end) {
+					finished = true, flag = 0;	// no meeting point inside chunk c+1
+				} else {
+					// advance the chain that is behind (the true chain on a tie)
+					bool step_true = T.pos_q <= P.pos_q;
+					if (step_true != (a_true != 0)) {
+						WalkState tmp = A;
+						A = B, B = tmp;
+						a_true ^= 1u;
+					}
+					SharedAcc acc = {&cells[1][0][tid], a_true ? 1u : 0xffffffffu};
+					walk_step<QUARTER, SPEC>(S, q, t, A, acc);
+				}
+			}
+			if (finished) {
+				u32 *rec = records + unit * ANDI_UNIT_WORDS;
+#pragma unroll
+				for (int x = 0; x < 16; x++) rec[x] = cells[0][x][tid];
+#pragma unroll
+				for (int x = 0; x < 16; x++) rec[16 + x] = flag ? cells[1][x][tid] : 0u;
+				rec[32] = E.pos_q, rec[33] = E.last_s, rec[34] = E.last_q, rec[35] = E.last_len, rec[36] = E.paired;
+				rec[37] = flag;
+				active = false;
+				unit += stride;
+			}
+		}
+		__syncwarp();
+	}
+}
+
+// ---- k_walk_reduce: one thread per pair, see the header of this file.
+template <bool QUARTER, bool SPEC>
+__global__ void __launch_bounds__(128)
+k_walk_reduce(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
+			  u32 nq, u32 chunk, u32 cpq, u32 threshold, const u32 *__restrict__ records, u32 *__restrict__ out) {
+	u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= nq) return;
+	u32 qid = query_ids ? query_ids[k] : k;
+	u32 *cell = out + (size_t)k * 17;
+	if (qid == S.self) {
+		// src/dist_hack.h:61-64
+		cell[0] = 9;
+		for (int c = 1; c < 16; c++) cell[c] = 0;
+		cell[16] = 9;
+		return;
+	}
+	const TextView q = queries[qid].t;
+	const u32 t = threshold, qlen = q.len;
+	const u32 nch = (u32)(((unsigned long long)qlen + chunk - 1) / chunk);
+	LocalAcc total;
+#pragma unroll
+	for (int x = 0; x < 16; x++) total.c[x] = 0;
+	WalkState fin = amnesic_state(0);
+	u32 c = 0;
+	while (c < nch) {
+		const u32 *rec = records + ((unsigned long long)k * cpq + c) * ANDI_UNIT_WORDS;
+#pragma unroll
+		for (int x = 0; x < 16; x++) total.c[x] += rec[x] + rec[16 + x];
+		fin.pos_q = rec[32], fin.last_s = rec[33], fin.last_q = rec[34], fin.last_len = rec[35], fin.paired = rec[36];
+		if (rec[37]) {
+			c++;
 			continue;
 		}
-		const TextView q = queries[qid].t;
-		walk_pair<QUARTER, SPEC>(S, q, threshold_override ? threshold_override : S.threshold, cell);
+		// The boundary into chunk c+1 did not synchronise: carry the true chain on from E_c.
+		WalkState T = fin;
+		bool resumed = false;
+		while (T.pos_q < qlen) {
+			u32 cc = T.pos_q / chunk;  // chunk the true chain is in
+			u32 cc_end = (u32)min((unsigned long long)qlen, (unsigned long long)(cc + 1) * chunk);
+			WalkState P = amnesic_state(cc * chunk);
+			LocalAcc minus;
+#pragma unroll
+			for (int x = 0; x < 16; x++) minus.c[x] = 0;
+			bool met = false;
+			for (;;) {
+				if (same_state(T, P)) {
+					met = true;
+					break;
+				}
+				if (T.pos_q >= cc_end || P.pos_q >= cc_end) break;
+				if (T.pos_q <= P.pos_q)
+					walk_step<QUARTER, SPEC>(S, q, t, T, total);
+				else
+					walk_step<QUARTER, SPEC>(S, q, t, P, minus);
+			}
+			if (met) {
+				// from here the amnesic walk of chunk cc IS the true walk: take its record, minus
+				// what the amnesic chain had counted before the meeting point
+#pragma unroll
+				for (int x = 0; x < 16; x++) total.c[x] -= minus.c[x];
+				c = cc;
+				resumed = true;
+				break;
+			}
+			// leave chunk cc with the true chain alone
+			while (T.pos_q < cc_end) walk_step<QUARTER, SPEC>(S, q, t, T, total);
+		}
+		if (!resumed) {
+			fin = T;
+			break;
+		}
 	}
+	walk_tail<QUARTER, SPEC>(q, t, fin, total);
+#pragma unroll
+	for (int x = 0; x < 16; x++) cell[x] = total.c[x];
+	cell[16] = qlen;
 }
 
 // get_match for a batch of packed queries (tests / andi_esa_get_match): the lookup of the walk

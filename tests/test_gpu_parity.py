@@ -154,3 +154,16 @@ def test_medium_genomes_with_properties(ctx):
     ctx.set_pool(ident)
     g2 = ctx.dist_rows(s_begin=0, s_end=1)
     assert g2[0, 1, :16].sum() == len(seqs[1]) and g2[0, 1, [0, 5, 10, 15]].sum() == len(seqs[1])
+
+
+@pytest.mark.parametrize("chunk", [64, 257, 1000, 4096])
+def test_chunk_boundaries_are_exact(ctx, chunk, monkeypatch):
+    """The chunked walk must not depend on where the chunk boundaries fall (walk_kernels.cuh):
+    odd chunk lengths, chunks shorter than an anchor, chunks longer than the sequences."""
+    monkeypatch.setenv("ANDI_B200_CHUNK", str(chunk))
+    for name, seqs in stress_sequences().items():
+        ctx.set_pool(seqs)
+        for model in ("JC", "LOGDET"):
+            got = ctx.dist_rows(model=model)
+            want = oracle.rows(seqs, model)
+            assert np.array_equal(got, want), (name, model, chunk)
