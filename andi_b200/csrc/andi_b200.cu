@@ -695,6 +695,32 @@ struct TempQueries {
 	bool any_sep = false;
 };
 
+// Many short queries (get_match batches): one thread packs one whole query.
+__global__ void k_pack_many(const unsigned char *__restrict__ chars, const size_t *__restrict__ coff,
+							const u32 *__restrict__ lens, const size_t *__restrict__ woff, u32 nq,
+							u64 *__restrict__ code, u64 *__restrict__ spec, unsigned long long *counters) {
+	u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= nq) return;
+	const unsigned char *src = chars + coff[k];
+	u32 n = lens[k], nw = n / 32 + 3, sep = 0;
+	for (u32 w = 0; w < nw; w++) {
+		u64 cw = 0, sw = 0;
+		for (u32 d = 0; d < 32 && w * 32 + d < n; d++) {
+			u32 c = src[w * 32 + d];
+			bool nuc = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
+			u32 v = c & 6u;
+			v ^= v >> 1;
+			v >>= 1;
+			if (!nuc) v = 0, sep++;
+			cw |= (u64)v << (2 * d);
+			sw |= (u64)(!nuc) << (2 * d);
+		}
+		code[woff[k] + w] = cw;
+		spec[woff[k] + w] = sw;
+	}
+	if (sep) atomicAdd(&counters[1], (unsigned long long)sep);
+}
+
 static int temp_queries(andi_ctx *ctx, const char *const *qs, const size_t *lens, size_t nq, TempQueries &T) {
 	std::vector<size_t> coff(nq), woff(nq);
 	size_t chars = 0, words = 0;
@@ -713,12 +739,37 @@ static int temp_queries(andi_ctx *ctx, const char *const *qs, const size_t *lens
 	CK(cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
 	std::vector<QueryView> qv(nq);
 	for (size_t k = 0; k < nq; k++) {
-		if (lens[k]) CK(cudaMemcpyAsync(d_chars + coff[k], qs[k], lens[k], cudaMemcpyHostToDevice, ctx->stream));
-		u32 nw = (u32)plane_words(lens[k]);
-		k_pack<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(d_chars + coff[k], (u32)lens[k], T.code + woff[k],
-														   T.spec + woff[k], nw, d_cnt);
 		qv[k].t.code = T.code + woff[k], qv[k].t.spec = T.spec + woff[k];
 		qv[k].t.len = (u32)lens[k], qv[k].t.mid = 0xffffffffu, qv[k].has_sep = 0;
+	}
+	if (nq <= 8) {
+		for (size_t k = 0; k < nq; k++) {
+			if (lens[k]) CK(cudaMemcpyAsync(d_chars + coff[k], qs[k], lens[k], cudaMemcpyHostToDevice, ctx->stream));
+			u32 nw = (u32)plane_words(lens[k]);
+			k_pack<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(d_chars + coff[k], (u32)lens[k], T.code + woff[k],
+															   T.spec + woff[k], nw, d_cnt);
+		}
+	} else {
+		// gather on the host, one copy, one kernel
+		std::vector<unsigned char> host(chars);
+		std::vector<u32> l32(nq);
+		for (size_t k = 0; k < nq; k++) {
+			memcpy(host.data() + coff[k], qs[k], lens[k]);
+			l32[k] = (u32)lens[k];
+		}
+		size_t *d_coff = nullptr, *d_woff = nullptr;
+		u32 *d_len = nullptr;
+		CK(dalloc(ctx, &d_coff, nq));
+		CK(dalloc(ctx, &d_woff, nq));
+		CK(dalloc(ctx, &d_len, nq));
+		CK(cudaMemcpyAsync(d_chars, host.data(), chars, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(d_coff, coff.data(), nq * sizeof(size_t), cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(d_woff, woff.data(), nq * sizeof(size_t), cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(d_len, l32.data(), nq * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+		k_pack_many<<<nblocks(nq, 128), 128, 0, ctx->stream>>>(d_chars, d_coff, d_len, d_woff, (u32)nq, T.code, T.spec,
+																d_cnt);
+		CK(cudaStreamSynchronize(ctx->stream));	 // host staging buffers go out of scope
+		dfree(ctx, d_coff), dfree(ctx, d_woff), dfree(ctx, d_len);
 	}
 	ctx->st.h2d_bytes += chars;
 	unsigned long long cnt[2];
@@ -759,3 +810,6 @@ extern "C" int andi_esa_get_match(const andi_esa *E, const char *const *queries,
 
 // ------------------------------------------------------------------ the walk (host side)
 #include "walk_host.cuh"
+
+// ------------------------------------------------------------------ part B: reference symbols
+#include "compat.cuh"

@@ -141,7 +141,7 @@ def ref() -> C.CDLL:
     if _ref is None:
         if not REF_SO.exists():
             raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
-        L = C.CDLL(str(REF_SO), mode=C.RTLD_GLOBAL)
+        L = C.CDLL(str(REF_SO))
         L.seq_subject_init.argtypes = [C.POINTER(RefSubject), C.POINTER(RefSeq)]
         L.seq_subject_free.argtypes = [C.POINTER(RefSubject)]
         L.esa_init.argtypes = [C.POINTER(RefEsa), C.POINTER(RefSubject)]
