@@ -5,6 +5,7 @@
 // queries stream), which is also what F_LOW_MEMORY asks for; the parallelism comes from
 // splitting every query into chunks (walk_kernels.cuh).
 #pragma once
+#include "walk_fast.cuh"
 
 typedef void (*chunks_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, u32 *);
 typedef void (*reduce_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, const u32 *, u32 *);
@@ -53,6 +54,10 @@ static int launch_walk(andi_ctx *ctx, const SubjectIndex &S, const QueryView *d_
 	chunks_fn cf = nullptr;
 	reduce_fn rf = nullptr;
 	pick_walk(model, spec, cf, rf);
+	// headline configuration (RAW/JC/KIMURA counting, no separators): the micro-op kernel
+	const char *force = getenv("ANDI_B200_WALK");
+	bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
+	if (quarter && !spec && !(force && strcmp(force, "basic") == 0)) cf = k_walk_chunks_fast;
 	int per_sm = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf, ANDI_WALK_THREADS, 0));
 	if (per_sm < 1) per_sm = 1;
