@@ -1,22 +1,32 @@
 // andi_b200/csrc/walk_fast.cuh -- k_walk_chunks_fast: the chunked anchor walk of
-// walk_kernels.cuh as a lane-level micro-op machine.
+// walk_kernels.cuh as a phase pipeline with carry-over.
 //
 // Same units, same records, same results as k_walk_chunks<QUARTER=true, SPEC=false> (RAW / JC /
 // KIMURA counting, no '!' in subject or queries -- the headline configuration). What changes
-// is the execution shape. In the straightforward kernel every lane runs nested loops (window
-// compares of different lengths, bucket scans, bitmap probes) and the warp waits for its
-// slowest lane at every level: ncu showed 6 of 32 lanes active. Here every lane carries a tiny
-// program counter `op`; one trip of the single main loop performs for each lane exactly ONE
-// memory round -- a 32-base window op on two streams, or a directory / suffix-array / bitmap
-// probe -- followed by register-only transitions. Lanes never wait for another lane's loop.
+// is the execution shape. In the straightforward kernel every lane runs nested while-loops
+// (window compares of different lengths, bucket scans, bitmap probes) and the warp waits for
+// its slowest lane at every level: ncu showed 6 of 32 lanes active. A pure lane-level state
+// machine (one op per lane per trip) does not fix that either: lanes drift apart and every
+// state's code runs with the few lanes that happen to be in it (measured: 7 of 32).
 //
-//   OP_BEGIN  chunk/phase bookkeeping, then set up the lucky compare (process.c:86-99)
-//   OP_CMP    one 32-base window of a compare (lucky diagonal or directory candidate)
-//   OP_DIR    k-mer directory probe        OP_CAND  fetch SA[candidate]
-//   OP_BITS   presence bitmaps (match shorter than K)
-//   OP_COLS   classify up to 32 gap columns (model.c:309-337)
-//   OP_SLOW   anything unusual -> longest_match<false>() of walk_kernels.cuh
-//   DECIDE    (not a memory op) process.c:160-196: pairing, accounting, advance
+// Here one trip of the main loop is a FIXED sequence of phases, each executed at most once:
+//
+//   BEGIN -> CMP (window 1) -> DIR -> CAND -> CMP (window 2 / candidate) -> BITS -> SLOW
+//         -> DECIDE -> COLS
+//
+// A lane flows through as many consecutive phases as its walk step needs -- the common steps
+// (lucky anchor within two windows; lucky miss -> directory -> one candidate) complete in ONE
+// trip -- and only carries over into the next trip when it needs a phase again (a long
+// compare, a second candidate, more gap columns). Nobody waits for a loop, and lanes stay
+// aligned at step boundaries, so BEGIN / CMP / DECIDE run with most of the warp.
+//
+//   BEGIN   chunk/phase bookkeeping, then set up the lucky compare (process.c:86-99)
+//   CMP     one 32-base window of a compare (lucky diagonal or directory candidate)
+//   DIR     k-mer directory probe          CAND   fetch SA[candidate]
+//   BITS    presence bitmaps (match shorter than K)
+//   SLOW    anything unusual -> longest_match<false>() of walk_kernels.cuh
+//   DECIDE  process.c:160-196: pairing, accounting, advance
+//   COLS    classify up to 32 gap columns (model.c:309-337)
 //
 // The single-column gap -- by far the most common one, a lone substitution between two
 // anchors -- costs no memory op at all: the class of the column that ended a compare is
@@ -32,6 +42,80 @@ struct WordCache {
 	u32 idx;	 // word index of w0 (0xfffffff0 = empty; idx + 1 must not wrap to a valid index)
 	u64 w0, w1;	 // words idx and idx+1
 };
+
+// 32 characters starting at pos through a two-word register cache: consecutive windows of a
+// stream reload one word, a window inside the cached pair reloads nothing.
+__device__ __forceinline__ u64 cached_window(WordCache &c, const u64 *__restrict__ words, u32 pos) {
+	u32 i = pos >> 5;
+	bool h0 = i == c.idx, h1 = i == c.idx + 1u;
+	if (h1) c.w0 = c.w1;
+	if (!(h0 | h1)) c.w0 = __ldg(words + i);
+	if (!h0) c.w1 = __ldg(words + i + 1);
+	c.idx = i;
+	u32 sh = (pos & 31u) * 2u;
+	return sh ? (c.w0 >> sh) | (c.w1 << (64u - sh)) : c.w0;
+}
+
+struct LaneCompare {
+	u32 cs, ck, clim, is_cand;	// subject start, matched so far, limit, lucky(0)/candidate(1)
+};
+
+struct LaneLookup {
+	u32 key, cand, hi, best, best_p, best_cnt, best_mm, bits_m;
+};
+
+struct LaneResult {
+	u32 s, len, mm, found;
+};
+
+// One 32-base window of the current compare; sets `op` when the compare has ended.
+__device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &L, LaneResult &R, WordCache &qc,
+										   WordCache &sc, const u64 *__restrict__ q_code,
+										   const u64 *__restrict__ s_code, u32 a_pos, u32 qlen, u32 t, int K) {
+	u64 qw = cached_window(qc, q_code, a_pos + C.ck);
+	u64 sw = cached_window(sc, s_code, C.cs + C.ck);
+	if (C.ck == 0 && !C.is_cand) L.key = K > 0 ? kmer_key(qw, K) : 0u;
+	u32 left = C.clim - C.ck;
+	u64 x = qw ^ sw;
+	x = (x | (x >> 1)) & ANDI_EVEN_BITS;
+	if (left < 32u) x |= 1ULL << (2u * left);
+	u32 len, mm = 0;
+	if (x) {
+		u32 d = (u32)(__ffsll((long long)x) - 1) >> 1;
+		len = C.ck + d;
+		if (d < left) mm = ANDI_MM_VALID | ((((u32)(sw >> (2u * d))) & 3u) << 2) | (((u32)(qw >> (2u * d))) & 3u);
+	} else {
+		C.ck += 32u;
+		if (C.ck != C.clim) return;	 // compare continues
+		len = C.clim;
+	}
+	if (!C.is_cand) {
+		if (len >= t) {
+			R.found = 1, R.s = C.cs, R.len = len, R.mm = mm;
+			op = OP_DECIDE;
+		} else if (K > 0 && qlen - a_pos >= (u32)K) {
+			op = OP_DIR;  // process.c:117: longest match anywhere in RS
+		} else {
+			op = OP_SLOW;
+		}
+	} else {
+		if (len > L.best)
+			L.best = len, L.best_cnt = 1, L.best_p = C.cs, L.best_mm = mm;
+		else if (len == L.best)
+			L.best_cnt++;
+		L.cand++;
+		if (L.cand < L.hi) {
+			op = OP_CAND;
+		} else if (L.best >= (u32)K) {
+			R.found = (L.best_cnt == 1 && L.best >= t) ? 1u : 0u;
+			R.s = L.best_p, R.len = L.best, R.mm = L.best_mm;
+			op = OP_DECIDE;
+		} else {
+			L.bits_m = (u32)(K - 1);
+			op = OP_BITS;
+		}
+	}
+}
 
 __global__ void __launch_bounds__(ANDI_WALK_THREADS, 3)
 k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
@@ -53,19 +137,15 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 	u32 a_pos = 0, a_ls = 0, a_lq = 0, a_ll = 0, a_pm = 0;
 	u32 b_pos = 0, b_ls = 0, b_lq = 0, b_ll = 0, b_pm = 0;
 	u32 set = 0, sign = 1;
-	// current compare
-	u32 cs = 0, ck = 0, clim = 0, cand_cmp = 0;
-	// current lookup
-	u32 key = 0, cand = 0, hi = 0, best = 0, best_p = 0, best_cnt = 0, best_mm = 0, bits_m = 0;
-	// result handed to DECIDE
-	u32 cur_s = 0, cur_len = 0, cur_mm = 0, found = 0;
-	// gap columns
+	LaneCompare C = {0, 0, 0, 0};
+	LaneLookup L = {0, 0, 0, 0, 0, 0, 0, 0};
+	LaneResult R = {0, 0, 0, 0};
 	u32 cols_s = 0, cols_q = 0, cols_left = 0;
 	WordCache qc, sc;
 	qc.idx = sc.idx = 0xfffffff0u, qc.w0 = qc.w1 = sc.w0 = sc.w1 = 0;
 
 	for (;;) {
-		// ------------------------------------------------------------ (0) unit fetch
+		// ------------------------------------------------------------ FETCH
 		if (op == OP_FETCH) {
 			op = OP_IDLE;
 			while (unit < total) {
@@ -91,7 +171,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 		}
 		if (__all_sync(0xffffffffu, op == OP_IDLE)) break;
 
-		// ------------------------------------------------------------ (1) step set-up
+		// ------------------------------------------------------------ BEGIN
 		if (op == OP_BEGIN) {
 			bool finished = false;
 			u32 flag = 1;
@@ -141,175 +221,94 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 				u32 gap = advance - a_ll;
 				u32 guess = a_ls + advance;
 				if (guess < N && gap <= t) {
-					cs = guess;
+					C.cs = guess;
 					u32 run = guess < mid ? mid - guess : (guess == mid ? 0u : N - guess);
-					clim = min(rem, run);
+					C.clim = min(rem, run);
 				} else {
-					cs = 0, clim = 0;  // no lucky attempt: the window op only fetches the query k-mer
+					C.cs = 0, C.clim = 0;  // no lucky attempt: the window op only fetches the query k-mer
 				}
-				ck = 0, cand_cmp = 0;
+				C.ck = 0, C.is_cand = 0;
 				op = OP_CMP;
 			}
 		}
 
-		// ------------------------------------------------------------ (2) one memory round
-		const bool text_op = (op == OP_CMP) | (op == OP_COLS);
-		u32 ta = 0, tb = 0;	 // query / subject position of the window
-		if (text_op) {
-			ta = op == OP_CMP ? a_pos + ck : cols_q;
-			tb = op == OP_CMP ? cs + ck : cols_s;
-			u32 iq = ta >> 5, is = tb >> 5;
-			bool qh0 = iq == qc.idx, qh1 = iq == qc.idx + 1u;
-			bool sh0 = is == sc.idx, sh1 = is == sc.idx + 1u;
-			if (qh1) qc.w0 = qc.w1;
-			if (sh1) sc.w0 = sc.w1;
-			if (!(qh0 | qh1)) qc.w0 = __ldg(q_code + iq);
-			if (!qh0) qc.w1 = __ldg(q_code + iq + 1);
-			if (!(sh0 | sh1)) sc.w0 = __ldg(s_code + is);
-			if (!sh0) sc.w1 = __ldg(s_code + is + 1);
-			qc.idx = iq, sc.idx = is;
-		}
-		u32 t0 = 0, t1 = 0, t2 = 0;
+		// ------------------------------------------------------------ CMP, first window of the trip
+		if (op == OP_CMP) cmp_window(op, C, L, R, qc, sc, q_code, s_code, a_pos, qlen, t, K);
+
+		// ------------------------------------------------------------ DIR
 		if (op == OP_DIR) {
-			t0 = __ldg(S.dir + key);
-			t1 = __ldg(S.dir + key + 1);
-		} else if (op == OP_CAND) {
-			t0 = __ldg(S.SA + cand);
-		} else if (op == OP_BITS) {
-			u32 x0 = key >> (2 * (K - (int)bits_m));
-			t0 = __ldg(S.present.bits + S.present.offset[bits_m] + (x0 >> 5)) >> (x0 & 31u);
-			if (bits_m >= 2) {
-				u32 x1 = x0 >> 2;
-				t1 = __ldg(S.present.bits + S.present.offset[bits_m - 1] + (x1 >> 5)) >> (x1 & 31u);
-			}
-			if (bits_m >= 3) {
-				u32 x2 = x0 >> 4;
-				t2 = __ldg(S.present.bits + S.present.offset[bits_m - 2] + (x2 >> 5)) >> (x2 & 31u);
+			u32 t0 = __ldg(S.dir + L.key), t1 = __ldg(S.dir + L.key + 1);
+			if (t1 > t0) {
+				if (t1 - t0 <= ANDI_SCAN_MAX) {
+					L.cand = t0, L.hi = t1, L.best = 0, L.best_cnt = 0, L.best_p = 0, L.best_mm = 0;
+					op = OP_CAND;
+				} else {
+					op = OP_SLOW;
+				}
+			} else {
+				L.bits_m = (u32)(K - 1);
+				op = OP_BITS;
 			}
 		}
 
-		// ------------------------------------------------------------ (3) consume
-		u32 nop = op;
-		if (op == OP_CMP) {
-			u32 shq = (ta & 31u) * 2u, shs = (tb & 31u) * 2u;
-			u64 qw = shq ? (qc.w0 >> shq) | (qc.w1 << (64u - shq)) : qc.w0;
-			u64 sw = shs ? (sc.w0 >> shs) | (sc.w1 << (64u - shs)) : sc.w0;
-			if (ck == 0 && !cand_cmp) key = K > 0 ? kmer_key(qw, K) : 0u;
-			u32 left = clim - ck;
-			u64 x = qw ^ sw;
-			x = (x | (x >> 1)) & ANDI_EVEN_BITS;
-			if (left < 32u) x |= 1ULL << (2u * left);
-			bool ended = false;
-			u32 len = 0, mm = 0;
-			if (x) {
-				u32 d = (u32)(__ffsll((long long)x) - 1) >> 1;
-				len = ck + d;
-				ended = true;
-				if (d < left) mm = ANDI_MM_VALID | ((((u32)(sw >> (2u * d))) & 3u) << 2) | (((u32)(qw >> (2u * d))) & 3u);
-			} else {
-				ck += 32u;
-				if (ck == clim) ended = true, len = clim;
-			}
-			if (ended) {
-				if (!cand_cmp) {
-					if (len >= t) {
-						found = 1, cur_s = cs, cur_len = len, cur_mm = mm;
-						nop = OP_DECIDE;
-					} else if (K > 0 && qlen - a_pos >= (u32)K) {
-						nop = OP_DIR;  // process.c:117: longest match anywhere in RS
-					} else {
-						nop = OP_SLOW;
-					}
-				} else {
-					if (len > best)
-						best = len, best_cnt = 1, best_p = cs, best_mm = mm;
-					else if (len == best)
-						best_cnt++;
-					cand++;
-					if (cand < hi) {
-						nop = OP_CAND;
-					} else if (best >= (u32)K) {
-						found = (best_cnt == 1 && best >= t) ? 1u : 0u;
-						cur_s = best_p, cur_len = best, cur_mm = best_mm;
-						nop = OP_DECIDE;
-					} else {
-						bits_m = (u32)(K - 1);
-						nop = OP_BITS;
-					}
-				}
-			}
-		} else if (op == OP_DIR) {
-			if (t1 > t0) {
-				if (t1 - t0 <= ANDI_SCAN_MAX) {
-					cand = t0, hi = t1, best = 0, best_cnt = 0, best_p = 0, best_mm = 0;
-					nop = OP_CAND;
-				} else {
-					nop = OP_SLOW;
-				}
-			} else {
-				bits_m = (u32)(K - 1);
-				nop = OP_BITS;
-			}
-		} else if (op == OP_CAND) {
-			u32 p = t0, rem = qlen - a_pos;
+		// ------------------------------------------------------------ CAND
+		if (op == OP_CAND) {
+			u32 p = __ldg(S.SA + L.cand), rem = qlen - a_pos;
 			u32 run = p < mid ? mid - p : (p == mid ? 0u : N - p);
-			cs = p, ck = 0, clim = min(rem, run), cand_cmp = 1;
-			nop = OP_CMP;
-		} else if (op == OP_BITS) {
+			C.cs = p, C.ck = 0, C.clim = min(rem, run), C.is_cand = 1;
+			op = OP_CMP;
+		}
+
+		// ------------------------------------------------------------ CMP, second window / candidate
+		if (op == OP_CMP) cmp_window(op, C, L, R, qc, sc, q_code, s_code, a_pos, qlen, t, K);
+
+		// ------------------------------------------------------------ BITS
+		if (op == OP_BITS) {
+			u32 m = L.bits_m;
+			u32 x0 = L.key >> (2 * (K - (int)m));
+			u32 t0 = __ldg(S.present.bits + S.present.offset[m] + (x0 >> 5)) >> (x0 & 31u), t1 = 0, t2 = 0;
+			if (m >= 2) {
+				u32 x1 = x0 >> 2;
+				t1 = __ldg(S.present.bits + S.present.offset[m - 1] + (x1 >> 5)) >> (x1 & 31u);
+			}
+			if (m >= 3) {
+				u32 x2 = x0 >> 4;
+				t2 = __ldg(S.present.bits + S.present.offset[m - 2] + (x2 >> 5)) >> (x2 & 31u);
+			}
 			u32 l = 0;
 			bool done = true;
 			if (t0 & 1u)
-				l = bits_m;
-			else if (bits_m >= 2 && (t1 & 1u))
-				l = bits_m - 1;
-			else if (bits_m >= 3 && (t2 & 1u))
-				l = bits_m - 2;
-			else if (bits_m > 3)
-				bits_m -= 3, done = false;
+				l = m;
+			else if (m >= 2 && (t1 & 1u))
+				l = m - 1;
+			else if (m >= 3 && (t2 & 1u))
+				l = m - 2;
+			else if (m > 3)
+				L.bits_m = m - 3, done = false;
 			if (done) {
-				found = 0, cur_len = l, cur_s = 0, cur_mm = 0;
-				nop = OP_DECIDE;
+				R.found = 0, R.len = l, R.s = 0, R.mm = 0;
+				op = OP_DECIDE;
 			}
-		} else if (op == OP_COLS) {
-			u32 span = min(32u, cols_left);
-			u32 shq = (ta & 31u) * 2u, shs = (tb & 31u) * 2u;
-			u64 qw = shq ? (qc.w0 >> shq) | (qc.w1 << (64u - shq)) : qc.w0;
-			u64 sw = shs ? (sc.w0 >> shs) | (sc.w1 << (64u - shs)) : sc.w0;
-			u64 valid = span == 32u ? ANDI_EVEN_BITS : (ANDI_EVEN_BITS & ((1ULL << (2u * span)) - 1ULL));
-			if (cols_s <= mid && mid - cols_s < span) valid &= ~(1ULL << (2u * (mid - cols_s)));  // '#' column
-			u64 x = qw ^ sw;
-			u64 neq = (x | (x >> 1)) & valid, eq = valid & ~neq;
-			u64 lo = qw & ANDI_EVEN_BITS, hb = (qw >> 1) & ANDI_EVEN_BITS;
-			u32 *col = &cells[set][0][tid];
-			col[0 * ANDI_WALK_THREADS] += (u32)__popcll(eq & ~hb & ~lo) * sign;
-			col[5 * ANDI_WALK_THREADS] += (u32)__popcll(eq & ~hb & lo) * sign;
-			col[10 * ANDI_WALK_THREADS] += (u32)__popcll(eq & hb & ~lo) * sign;
-			col[15 * ANDI_WALK_THREADS] += (u32)__popcll(eq & hb & lo) * sign;
-			while (neq) {
-				u32 d2 = (u32)(__ffsll((long long)neq) - 1);
-				neq &= neq - 1;
-				u32 cls = ((((u32)(sw >> d2)) & 3u) << 2) | (((u32)(qw >> d2)) & 3u);
-				col[cls * ANDI_WALK_THREADS] += sign;
-			}
-			cols_s += span, cols_q += span, cols_left -= span;
-			if (cols_left == 0) nop = OP_BEGIN;
-		} else if (op == OP_SLOW) {
+		}
+
+		// ------------------------------------------------------------ SLOW (rare)
+		if (op == OP_SLOW) {
 			TextView qv;
 			qv.code = q_code, qv.spec = nullptr, qv.len = qlen, qv.mid = 0xffffffffu;
 			MatchResult m = longest_match<false>(S, qv, a_pos, qlen - a_pos);
-			found = (m.unique && m.len >= t) ? 1u : 0u;
-			cur_len = m.len, cur_mm = 0;
-			cur_s = found ? __ldg(S.SA + m.at) : 0u;
-			nop = OP_DECIDE;
+			R.found = (m.unique && m.len >= t) ? 1u : 0u;
+			R.len = m.len, R.mm = 0;
+			R.s = R.found ? __ldg(S.SA + m.at) : 0u;
+			op = OP_DECIDE;
 		}
 
-		// ------------------------------------------------------------ (4) process.c:160-196
-		if (nop == OP_DECIDE) {
+		// ------------------------------------------------------------ DECIDE: process.c:160-196
+		if (op == OP_DECIDE) {
 			bool need_cols = false;
-			if (found) {
+			if (R.found) {
 				u32 *col = &cells[set][0][tid];
 				u32 end_s = a_ls + a_ll, end_q = a_lq + a_ll;
-				bool pairs = cur_s > end_s && (a_pos - end_q) == (cur_s - end_s) && ((cur_s < border) == (a_ls < border));
+				bool pairs = R.s > end_s && (a_pos - end_q) == (R.s - end_s) && ((R.s < border) == (a_ls < border));
 				bool count_last = pairs || (a_pm & 1u) || a_ll >= 2u * t;
 				if (count_last) {  // model.c:247-254
 					u32 f = (a_ll >> 2) * sign;
@@ -328,12 +327,35 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 						need_cols = true;
 					}
 				}
-				a_ls = cur_s, a_lq = a_pos, a_ll = cur_len;
-				a_pm = (pairs ? 1u : 0u) | (cur_mm << 1);
+				a_ls = R.s, a_lq = a_pos, a_ll = R.len;
+				a_pm = (pairs ? 1u : 0u) | (R.mm << 1);
 			}
-			a_pos += cur_len + 1u;
-			nop = need_cols ? OP_COLS : OP_BEGIN;
+			a_pos += R.len + 1u;
+			op = need_cols ? OP_COLS : OP_BEGIN;
 		}
-		op = nop;
+
+		// ------------------------------------------------------------ COLS: model.c:309-337
+		if (op == OP_COLS) {
+			u32 span = min(32u, cols_left);
+			u64 qw = window32(q_code, cols_q), sw = window32(s_code, cols_s);
+			u64 valid = span == 32u ? ANDI_EVEN_BITS : (ANDI_EVEN_BITS & ((1ULL << (2u * span)) - 1ULL));
+			if (cols_s <= mid && mid - cols_s < span) valid &= ~(1ULL << (2u * (mid - cols_s)));  // '#' column
+			u64 x = qw ^ sw;
+			u64 neq = (x | (x >> 1)) & valid, eq = valid & ~neq;
+			u64 lo = qw & ANDI_EVEN_BITS, hb = (qw >> 1) & ANDI_EVEN_BITS;
+			u32 *col = &cells[set][0][tid];
+			col[0 * ANDI_WALK_THREADS] += (u32)__popcll(eq & ~hb & ~lo) * sign;
+			col[5 * ANDI_WALK_THREADS] += (u32)__popcll(eq & ~hb & lo) * sign;
+			col[10 * ANDI_WALK_THREADS] += (u32)__popcll(eq & hb & ~lo) * sign;
+			col[15 * ANDI_WALK_THREADS] += (u32)__popcll(eq & hb & lo) * sign;
+			while (neq) {
+				u32 d2 = (u32)(__ffsll((long long)neq) - 1);
+				neq &= neq - 1;
+				u32 cls = ((((u32)(sw >> d2)) & 3u) << 2) | (((u32)(qw >> d2)) & 3u);
+				col[cls * ANDI_WALK_THREADS] += sign;
+			}
+			cols_s += span, cols_q += span, cols_left -= span;
+			if (cols_left == 0) op = OP_BEGIN;
+		}
 	}
 }

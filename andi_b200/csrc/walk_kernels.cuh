@@ -65,7 +65,7 @@ __device__ MatchResult search_range(const SubjectIndex &S, const TextView &q, u3
 		if (c == rem)
 			suffix_less = false;  // the query is a prefix of this suffix
 		else
-			suffix_less = sym3<SPEC>(S.rs, p + c) < sym3<true>(q, qpos + c);
+			suffix_less = sym3<SPEC>(S.rs, p + c) < sym3<SPEC>(q, qpos + c);  // q.mid is never hit
 		if (suffix_less)
 			lo = mid + 1;
 		else
