@@ -117,7 +117,10 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 	}
 }
 
-__global__ void __launch_bounds__(ANDI_WALK_THREADS, 3)
+#ifndef ANDI_FAST_BLOCKS_PER_SM
+#define ANDI_FAST_BLOCKS_PER_SM 4
+#endif
+__global__ void __launch_bounds__(ANDI_WALK_THREADS, ANDI_FAST_BLOCKS_PER_SM)
 k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
 				   u32 nq, u32 chunk, u32 cpq, u32 threshold, u32 *__restrict__ records) {
 	__shared__ u32 cells[2][16][ANDI_WALK_THREADS];
@@ -171,6 +174,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 		}
 		if (__all_sync(0xffffffffu, op == OP_IDLE)) break;
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ BEGIN
 		if (op == OP_BEGIN) {
 			bool finished = false;
@@ -232,9 +236,11 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 			}
 		}
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ CMP, first window of the trip
 		if (op == OP_CMP) cmp_window(op, C, L, R, qc, sc, q_code, s_code, a_pos, qlen, t, K);
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ DIR
 		if (op == OP_DIR) {
 			u32 t0 = __ldg(S.dir + L.key), t1 = __ldg(S.dir + L.key + 1);
@@ -251,6 +257,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 			}
 		}
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ CAND
 		if (op == OP_CAND) {
 			u32 p = __ldg(S.SA + L.cand), rem = qlen - a_pos;
@@ -259,9 +266,11 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 			op = OP_CMP;
 		}
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ CMP, second window / candidate
 		if (op == OP_CMP) cmp_window(op, C, L, R, qc, sc, q_code, s_code, a_pos, qlen, t, K);
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ BITS
 		if (op == OP_BITS) {
 			u32 m = L.bits_m;
@@ -291,6 +300,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 			}
 		}
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ SLOW (rare)
 		if (op == OP_SLOW) {
 			TextView qv;
@@ -302,6 +312,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 			op = OP_DECIDE;
 		}
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ DECIDE: process.c:160-196
 		if (op == OP_DECIDE) {
 			bool need_cols = false;
@@ -334,6 +345,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 			op = need_cols ? OP_COLS : OP_BEGIN;
 		}
 
+		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ COLS: model.c:309-337
 		if (op == OP_COLS) {
 			u32 span = min(32u, cols_left);
