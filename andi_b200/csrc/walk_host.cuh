@@ -72,7 +72,7 @@ static int launch_walk(andi_ctx *ctx, const SubjectIndex &S, const QueryView *d_
 	}
 	cf<<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
 													 d_records);
-	rf<<<nblocks(nq, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
+	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
 												   d_records, d_out);
 	mark(ctx, e1);
 	ctx->walk_ev.emplace_back(e0, e1);

@@ -12,7 +12,7 @@
 //                  the amnesic walk of chunk c+1, one step at a time, until both chains are in
 //                  the same WalkState. The counts of the true chain minus those of the amnesic
 //                  chain up to that point are the boundary correction D_c.
-//   k_walk_reduce  one thread per pair: total = sum_c (U_c + D_c) while every boundary
+//   k_walk_reduce  one warp per pair: total = sum_c (U_c + D_c) while every boundary
 //                  synchronised; where one did not (e.g. a long anchor-free stretch) it walks on
 //                  sequentially from the last known true state until the chains meet again.
 //
@@ -381,82 +381,102 @@ k_walk_chunks(const SubjectIndex S, const QueryView *__restrict__ queries, const
 	}
 }
 
-// ---- k_walk_reduce: one thread per pair, see the header of this file.
+// ---- k_walk_reduce: one WARP per pair, see the header of this file. Lanes sum the records
+// of 32 consecutive chunks at a time; the first boundary that did not synchronise (if any) is
+// located with a ballot and lane 0 carries the true chain on sequentially from there.
 template <bool QUARTER, bool SPEC>
 __global__ void __launch_bounds__(128)
 k_walk_reduce(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
 			  u32 nq, u32 chunk, u32 cpq, u32 threshold, const u32 *__restrict__ records, u32 *__restrict__ out) {
-	u32 k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= nq) return;
+	const u32 lane = threadIdx.x & 31u;
+	const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (k >= nq) return;  // whole warp
 	u32 qid = query_ids ? query_ids[k] : k;
 	u32 *cell = out + (size_t)k * 17;
 	if (qid == S.self) {
 		// src/dist_hack.h:61-64
-		cell[0] = 9;
-		for (int c = 1; c < 16; c++) cell[c] = 0;
-		cell[16] = 9;
+		if (lane < 17) cell[lane] = (lane == 0 || lane == 16) ? 9u : 0u;
 		return;
 	}
 	const TextView q = queries[qid].t;
 	const u32 t = threshold, qlen = q.len;
 	const u32 nch = (u32)(((unsigned long long)qlen + chunk - 1) / chunk);
-	LocalAcc total;
+	const u32 *base = records + (unsigned long long)k * cpq * ANDI_UNIT_WORDS;
+	LocalAcc total;	 // per lane partial sums
 #pragma unroll
 	for (int x = 0; x < 16; x++) total.c[x] = 0;
-	WalkState fin = amnesic_state(0);
-	u32 c = 0;
-	while (c < nch) {
-		const u32 *rec = records + ((unsigned long long)k * cpq + c) * ANDI_UNIT_WORDS;
+	WalkState fin = amnesic_state(0);  // meaningful on lane 0 only
+	bool have_fin = false;			   // lane 0: fin was produced by the sequential path at the very end
+	u32 c0 = 0;
+	while (c0 < nch) {
+		u32 c = c0 + lane;
+		bool valid = c < nch;
+		const u32 *rec = base + (unsigned long long)c * ANDI_UNIT_WORDS;
+		u32 flag = valid ? rec[37] : 1u;
+		unsigned bad = __ballot_sync(0xffffffffu, valid && !flag);
+		u32 first_bad = bad ? (u32)(__ffs((int)bad) - 1) : 32u;
+		if (valid && lane <= first_bad) {
 #pragma unroll
-		for (int x = 0; x < 16; x++) total.c[x] += rec[x] + rec[16 + x];
-		fin.pos_q = rec[32], fin.last_s = rec[33], fin.last_q = rec[34], fin.last_len = rec[35], fin.paired = rec[36];
-		if (rec[37]) {
-			c++;
+			for (int x = 0; x < 16; x++) total.c[x] += rec[x] + rec[16 + x];
+		}
+		if (!bad) {
+			c0 += 32;
 			continue;
 		}
-		// The boundary into chunk c+1 did not synchronise: carry the true chain on from E_c.
-		WalkState T = fin;
-		bool resumed = false;
-		while (T.pos_q < qlen) {
-			u32 cc = T.pos_q / chunk;  // chunk the true chain is in
-			u32 cc_end = (u32)min((unsigned long long)qlen, (unsigned long long)(cc + 1) * chunk);
-			WalkState P = amnesic_state(cc * chunk);
-			LocalAcc minus;
+		// The boundary after chunk cb did not synchronise: the true chain continues from E_cb.
+		u32 cb = c0 + first_bad;
+		u32 resume = 0xffffffffu;
+		if (lane == 0) {
+			const u32 *rb = base + (unsigned long long)cb * ANDI_UNIT_WORDS;
+			WalkState T;
+			T.pos_q = rb[32], T.last_s = rb[33], T.last_q = rb[34], T.last_len = rb[35], T.paired = rb[36];
+			while (T.pos_q < qlen) {
+				u32 cc = T.pos_q / chunk;  // chunk the true chain is in
+				u32 cc_end = (u32)min((unsigned long long)qlen, (unsigned long long)(cc + 1) * chunk);
+				WalkState P = amnesic_state(cc * chunk);
+				LocalAcc minus;
 #pragma unroll
-			for (int x = 0; x < 16; x++) minus.c[x] = 0;
-			bool met = false;
-			for (;;) {
-				if (same_state(T, P)) {
-					met = true;
+				for (int x = 0; x < 16; x++) minus.c[x] = 0;
+				bool met = false;
+				for (;;) {
+					if (same_state(T, P)) {
+						met = true;
+						break;
+					}
+					if (T.pos_q >= cc_end || P.pos_q >= cc_end) break;
+					if (T.pos_q <= P.pos_q)
+						walk_step<QUARTER, SPEC>(S, q, t, T, total);
+					else
+						walk_step<QUARTER, SPEC>(S, q, t, P, minus);
+				}
+				if (met) {
+					// from here the amnesic walk of chunk cc IS the true walk: take its record,
+					// minus what the amnesic chain had counted before the meeting point
+#pragma unroll
+					for (int x = 0; x < 16; x++) total.c[x] -= minus.c[x];
+					resume = cc;
 					break;
 				}
-				if (T.pos_q >= cc_end || P.pos_q >= cc_end) break;
-				if (T.pos_q <= P.pos_q)
-					walk_step<QUARTER, SPEC>(S, q, t, T, total);
-				else
-					walk_step<QUARTER, SPEC>(S, q, t, P, minus);
+				while (T.pos_q < cc_end) walk_step<QUARTER, SPEC>(S, q, t, T, total);
 			}
-			if (met) {
-				// from here the amnesic walk of chunk cc IS the true walk: take its record, minus
-				// what the amnesic chain had counted before the meeting point
-#pragma unroll
-				for (int x = 0; x < 16; x++) total.c[x] -= minus.c[x];
-				c = cc;
-				resumed = true;
-				break;
-			}
-			// leave chunk cc with the true chain alone
-			while (T.pos_q < cc_end) walk_step<QUARTER, SPEC>(S, q, t, T, total);
+			if (resume == 0xffffffffu) fin = T, have_fin = true;
 		}
-		if (!resumed) {
-			fin = T;
-			break;
-		}
+		resume = __shfl_sync(0xffffffffu, resume, 0);
+		if (resume == 0xffffffffu) break;  // the true chain reached the end of the query
+		c0 = resume;
 	}
-	walk_tail<QUARTER, SPEC>(q, t, fin, total);
+	if (lane == 0 && !have_fin) {
+		const u32 *rl = base + (unsigned long long)(nch - 1) * ANDI_UNIT_WORDS;
+		fin.pos_q = rl[32], fin.last_s = rl[33], fin.last_q = rl[34], fin.last_len = rl[35], fin.paired = rl[36];
+	}
+	if (lane == 0) walk_tail<QUARTER, SPEC>(q, t, fin, total);
 #pragma unroll
-	for (int x = 0; x < 16; x++) cell[x] = total.c[x];
-	cell[16] = qlen;
+	for (int x = 0; x < 16; x++) {
+		u32 v = total.c[x];
+		for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+		if (lane == 0) cell[x] = v;
+	}
+	if (lane == 0) cell[16] = qlen;
 }
 
 // get_match for a batch of packed queries (tests / andi_esa_get_match): the lookup of the walk

@@ -167,3 +167,35 @@ def test_chunk_boundaries_are_exact(ctx, chunk, monkeypatch):
             got = ctx.dist_rows(model=model)
             want = oracle.rows(seqs, model)
             assert np.array_equal(got, want), (name, model, chunk)
+
+
+def test_large_genomes_against_reference(ctx):
+    """20 Mbp genomes (N = 40 M): 32-bit index arithmetic, directory depth 13, several chunks
+    per thread. Checked against the reference itself (oracle/_ref) because the oracle's
+    doubling sorter is too slow at this size; skipped where _ref was not built."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    seqs = synth.star_phylogeny(2, 20_000_000, [0.0, 0.03], seed=4242)
+    want, _ = oracle.ref_rows(seqs, "JC", threads=2)
+    ctx.set_pool(seqs)
+    got = ctx.dist_rows()
+    assert np.array_equal(got, want)
+
+
+def test_very_large_genome_properties(ctx):
+    """120 Mbp (config 5 shape, N = 240 000 001): size-independent properties only -- identical
+    genomes are fully covered with no substitutions; a copy with k planted substitutions far
+    apart reports exactly k mismatches."""
+    n = 120_000_000
+    base = synth.base_genome(n, 99)
+    a = synth.ACGT[base].tobytes()
+    rng = np.random.default_rng(5)
+    pos = np.sort(rng.choice(n // 1000, size=500, replace=False)) * 1000 + 500
+    mut = base.copy()
+    mut[pos] = (mut[pos] + 1) & 3
+    b = synth.ACGT[mut].tobytes()
+    ctx.set_pool([a, a, b])
+    got = ctx.dist_rows(s_begin=0, s_end=1)
+    ident, sub = got[0, 1], got[0, 2]
+    assert ident[:16].sum() == n and ident[[0, 5, 10, 15]].sum() == n
+    assert sub[:16].sum() == n and sub[:16].sum() - sub[[0, 5, 10, 15]].sum() == 500
