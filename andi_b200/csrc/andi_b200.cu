@@ -53,6 +53,7 @@ struct andi_esa {
 	int32_t *LCP = nullptr;
 	u32 *dir = nullptr;
 	PresenceLevels present{};
+	unsigned char *plen = nullptr;
 	int K = 0;
 	bool has_sep = false;
 	bool full = false;
@@ -481,7 +482,10 @@ static int build_directory(andi_ctx *ctx, andi_esa *E) {
 																	   E->present.bits + E->present.offset[m]);
 	}
 	k_presence_patch<<<nblocks(E->N, 256), 256, 0, st>>>(rs, K, E->present);
-	ctx->st.esa_launches += 3 + (K - 1);
+	CK(dalloc(ctx, &E->plen, entries - 1));
+	k_prefix_len<<<nblocks(entries - 1, 256), 256, 0, st>>>(E->present, K, E->plen);
+	dfree(ctx, E->present.bits);  // only the table is needed from here on
+	ctx->st.esa_launches += 4 + (K - 1);
 	return ANDI_OK;
 }
 
@@ -523,7 +527,7 @@ static int build_full(andi_ctx *ctx, andi_esa *E) {
 static void esa_release(andi_esa *E) {
 	andi_ctx *ctx = E->ctx;
 	dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->SA), dfree(ctx, E->LCP);
-	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
+	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->plen), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
 	dfree(ctx, E->cache);
 }
 
@@ -683,7 +687,7 @@ extern "C" int andi_esa_download(const andi_esa *E, int32_t *SA, int32_t *LCP, i
 static SubjectIndex subject_index(const andi_esa *E) {
 	SubjectIndex S;
 	S.rs = rs_view(E);
-	S.SA = E->SA, S.LCP = E->LCP, S.dir = E->dir, S.present = E->present;
+	S.SA = E->SA, S.LCP = E->LCP, S.dir = E->dir, S.plen = E->plen;
 	S.K = E->K, S.threshold = E->threshold, S.self = E->self, S.has_sep = E->has_sep;
 	return S;
 }

@@ -325,6 +325,23 @@ __global__ void k_presence_patch(TextView rs, int K, PresenceLevels lv) {
 	}
 }
 
+// plen[x] for every k-mer x: length of the longest prefix of x (0 .. K-1) that occurs in RS.
+// This is what a lookup of an ABSENT k-mer returns, so the walk needs one byte load instead
+// of probing the bitmap levels.
+__global__ void k_prefix_len(PresenceLevels lv, int K, unsigned char *__restrict__ plen) {
+	u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= (1u << (2 * K))) return;
+	u32 l = 0;
+	for (int m = K - 1; m >= 1; m--) {
+		u32 y = x >> (2 * (K - m));
+		if ((lv.bits[lv.offset[m] + (y >> 5)] >> (y & 31u)) & 1u) {
+			l = (u32)m;
+			break;
+		}
+	}
+	plen[x] = (unsigned char)l;
+}
+
 // ------------------------------------------------------------------ E3: FVC
 // src/esa.c:229-245: FVC[i] = S[SA[i] + LCP[i]] as the original byte.
 __device__ __forceinline__ char byte_at(const TextView &rs, u32 pos) {

@@ -11,8 +11,8 @@
 //
 // Here one trip of the main loop is a FIXED sequence of phases, each executed at most once:
 //
-//   BEGIN -> CMP (window 1) -> DIR -> CAND -> CMP (window 2 / candidate) -> BITS -> SLOW
-//         -> DECIDE -> COLS
+//   BEGIN -> CMP (window 1) -> DIR -> CAND -> CMP (window 2 / candidate) -> SLOW -> DECIDE
+//         -> COLS
 //
 // A lane flows through as many consecutive phases as its walk step needs -- the common steps
 // (lucky anchor within two windows; lucky miss -> directory -> one candidate) complete in ONE
@@ -22,8 +22,7 @@
 //
 //   BEGIN   chunk/phase bookkeeping, then set up the lucky compare (process.c:86-99)
 //   CMP     one 32-base window of a compare (lucky diagonal or directory candidate)
-//   DIR     k-mer directory probe          CAND   fetch SA[candidate]
-//   BITS    presence bitmaps (match shorter than K)
+//   DIR     k-mer directory + prefix-length probe      CAND   fetch SA[candidate]
 //   SLOW    anything unusual -> longest_match<false>() of walk_kernels.cuh
 //   DECIDE  process.c:160-196: pairing, accounting, advance
 //   COLS    classify up to 32 gap columns (model.c:309-337)
@@ -34,7 +33,7 @@
 #pragma once
 #include "walk_kernels.cuh"
 
-enum : u32 { OP_FETCH = 0, OP_BEGIN, OP_CMP, OP_DIR, OP_CAND, OP_BITS, OP_COLS, OP_SLOW, OP_DECIDE, OP_IDLE };
+enum : u32 { OP_FETCH = 0, OP_BEGIN, OP_CMP, OP_DIR, OP_CAND, OP_COLS, OP_SLOW, OP_DECIDE, OP_IDLE };
 
 #define ANDI_MM_VALID 0x10u
 
@@ -45,12 +44,16 @@ struct WordCache {
 
 // 32 characters starting at pos through a two-word register cache: consecutive windows of a
 // stream reload one word, a window inside the cached pair reloads nothing.
-__device__ __forceinline__ u64 cached_window(WordCache &c, const u64 *__restrict__ words, u32 pos) {
+__device__ __forceinline__ u64 cached_window(WordCache &c, const u64 *__restrict__ words, u32 pos, u32 nwords) {
 	u32 i = pos >> 5;
 	bool h0 = i == c.idx, h1 = i == c.idx + 1u;
 	if (h1) c.w0 = c.w1;
 	if (!(h0 | h1)) c.w0 = __ldg(words + i);
-	if (!h0) c.w1 = __ldg(words + i + 1);
+	if (!h0) {
+		c.w1 = __ldg(words + i + 1);
+		// entering a new 32-byte sector: pull the line 512 bases ahead towards L2
+		if ((i & 3u) == 2u && i + 17u < nwords) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + i + 17));
+	}
 	c.idx = i;
 	u32 sh = (pos & 31u) * 2u;
 	return sh ? (c.w0 >> sh) | (c.w1 << (64u - sh)) : c.w0;
@@ -61,7 +64,7 @@ struct LaneCompare {
 };
 
 struct LaneLookup {
-	u32 key, cand, hi, best, best_p, best_cnt, best_mm, bits_m;
+	u32 key, cand, hi, best, best_p, best_cnt, best_mm, short_len;
 };
 
 struct LaneResult {
@@ -71,9 +74,9 @@ struct LaneResult {
 // One 32-base window of the current compare; sets `op` when the compare has ended.
 __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &L, LaneResult &R, WordCache &qc,
 										   WordCache &sc, const u64 *__restrict__ q_code,
-										   const u64 *__restrict__ s_code, u32 a_pos, u32 qlen, u32 t, int K) {
-	u64 qw = cached_window(qc, q_code, a_pos + C.ck);
-	u64 sw = cached_window(sc, s_code, C.cs + C.ck);
+										   const u64 *__restrict__ s_code, u32 s_words, u32 a_pos, u32 qlen, u32 t, int K) {
+	u64 qw = cached_window(qc, q_code, a_pos + C.ck, (qlen >> 5) + 3u);
+	u64 sw = cached_window(sc, s_code, C.cs + C.ck, s_words);
 	if (C.ck == 0 && !C.is_cand) L.key = K > 0 ? kmer_key(qw, K) : 0u;
 	u32 left = C.clim - C.ck;
 	u64 x = qw ^ sw;
@@ -111,8 +114,9 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 			R.s = L.best_p, R.len = L.best, R.mm = L.best_mm;
 			op = OP_DECIDE;
 		} else {
-			L.bits_m = (u32)(K - 1);
-			op = OP_BITS;
+			// only suffixes with a separator in their first K characters were in the range
+			R.found = 0, R.len = L.short_len, R.s = 0, R.mm = 0;
+			op = OP_DECIDE;
 		}
 	}
 }
@@ -238,12 +242,13 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ CMP, first window of the trip
-		if (op == OP_CMP) cmp_window(op, C, L, R, qc, sc, q_code, s_code, a_pos, qlen, t, K);
+		if (op == OP_CMP) cmp_window(op, C, L, R, qc, sc, q_code, s_code, (N >> 5) + 3u, a_pos, qlen, t, K);
 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ DIR
 		if (op == OP_DIR) {
 			u32 t0 = __ldg(S.dir + L.key), t1 = __ldg(S.dir + L.key + 1);
+			L.short_len = __ldg(S.plen + L.key);  // the answer if the k-mer turns out to be absent
 			if (t1 > t0) {
 				if (t1 - t0 <= ANDI_SCAN_MAX) {
 					L.cand = t0, L.hi = t1, L.best = 0, L.best_cnt = 0, L.best_p = 0, L.best_mm = 0;
@@ -252,8 +257,8 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 					op = OP_SLOW;
 				}
 			} else {
-				L.bits_m = (u32)(K - 1);
-				op = OP_BITS;
+				R.found = 0, R.len = L.short_len, R.s = 0, R.mm = 0;
+				op = OP_DECIDE;
 			}
 		}
 
@@ -268,37 +273,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ CMP, second window / candidate
-		if (op == OP_CMP) cmp_window(op, C, L, R, qc, sc, q_code, s_code, a_pos, qlen, t, K);
-
-		__syncwarp();  // phase boundary: every lane of the warp re-converges here
-		// ------------------------------------------------------------ BITS
-		if (op == OP_BITS) {
-			u32 m = L.bits_m;
-			u32 x0 = L.key >> (2 * (K - (int)m));
-			u32 t0 = __ldg(S.present.bits + S.present.offset[m] + (x0 >> 5)) >> (x0 & 31u), t1 = 0, t2 = 0;
-			if (m >= 2) {
-				u32 x1 = x0 >> 2;
-				t1 = __ldg(S.present.bits + S.present.offset[m - 1] + (x1 >> 5)) >> (x1 & 31u);
-			}
-			if (m >= 3) {
-				u32 x2 = x0 >> 4;
-				t2 = __ldg(S.present.bits + S.present.offset[m - 2] + (x2 >> 5)) >> (x2 & 31u);
-			}
-			u32 l = 0;
-			bool done = true;
-			if (t0 & 1u)
-				l = m;
-			else if (m >= 2 && (t1 & 1u))
-				l = m - 1;
-			else if (m >= 3 && (t2 & 1u))
-				l = m - 2;
-			else if (m > 3)
-				L.bits_m = m - 3, done = false;
-			if (done) {
-				R.found = 0, R.len = l, R.s = 0, R.mm = 0;
-				op = OP_DECIDE;
-			}
-		}
+		if (op == OP_CMP) cmp_window(op, C, L, R, qc, sc, q_code, s_code, (N >> 5) + 3u, a_pos, qlen, t, K);
 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ SLOW (rare)

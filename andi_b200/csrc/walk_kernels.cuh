@@ -31,7 +31,7 @@ struct SubjectIndex {
 	const u32 *SA;		   // N
 	const int32_t *LCP;	   // N + 1
 	const u32 *dir;		   // 4^K + 1
-	PresenceLevels present;
+	const unsigned char *plen;  // 4^K: longest prefix of each k-mer present in RS (< K)
 	int K;				   // directory depth, 0 = none (lookups use the generic search only)
 	u32 threshold;		   // minimum anchor length for this subject
 	u32 self;			   // pool index of the subject (its own query is skipped)
@@ -98,7 +98,7 @@ __device__ MatchResult search_range(const SubjectIndex &S, const TextView &q, u3
 
 // ---- the lookup the walk uses. Fast path: k-mer directory -> short scan of the bucket;
 // when the k-mer is absent only the LENGTH of the match matters (it is < K <= threshold, so
-// no anchor can result) and the presence bitmaps give it without touching the suffix array.
+// no anchor can result) and the plen table gives it without touching the suffix array.
 template <bool SPEC>
 __device__ __forceinline__ MatchResult longest_match(const SubjectIndex &S, const TextView &q, u32 qpos,
 													 u32 rem) {
@@ -135,14 +135,7 @@ __device__ __forceinline__ MatchResult longest_match(const SubjectIndex &S, cons
 		if (r.len >= (u32)K) return r;
 	}
 	MatchResult r;
-	r.unique = false, r.found_pos = false, r.at = 0, r.len = 0;
-	for (int m = K - 1; m >= 1; m--) {
-		u32 x = key >> (2 * (K - m));
-		if ((__ldg(S.present.bits + S.present.offset[m] + (x >> 5)) >> (x & 31u)) & 1u) {
-			r.len = (u32)m;
-			break;
-		}
-	}
+	r.unique = false, r.found_pos = false, r.at = 0, r.len = __ldg(S.plen + key);
 	return r;
 }
 

@@ -1,0 +1,119 @@
+"""CPU tests of the C host code behind the command line (andi_b200/host): estimators against
+the oracle (itself pinned to the reference), FASTA ingest, join mode."""
+import ctypes as C
+import gzip
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from andi_b200 import native
+
+ROOT = Path(__file__).resolve().parent.parent
+G = ROOT / "tests" / "golden"
+
+
+class HostSeq(C.Structure):
+    _fields_ = [("S", C.c_char_p), ("len", C.c_size_t), ("name", C.c_char_p)]
+
+
+class HostSeqs(C.Structure):
+    _fields_ = [("data", C.POINTER(HostSeq)), ("size", C.c_size_t), ("capacity", C.c_size_t)]
+
+
+@pytest.fixture(scope="module")
+def host():
+    L = C.CDLL(str(ROOT / "andi_b200" / "libandi_host.so"))
+    L.model_estimate.restype = C.c_double
+    L.model_estimate.argtypes = [C.POINTER(native.Model), C.c_int]
+    L.model_coverage.restype = C.c_double
+    L.model_coverage.argtypes = [C.POINTER(native.Model)]
+    L.model_average.restype = native.Model
+    L.model_average.argtypes = [C.POINTER(native.Model), C.POINTER(native.Model)]
+    L.fasta_read.argtypes = [C.c_char_p, C.POINTER(HostSeqs), C.POINTER(C.c_int)]
+    L.fasta_read_join.argtypes = [C.c_char_p, C.POINTER(HostSeqs), C.POINTER(C.c_int)]
+    L.seqs_init.argtypes = [C.POINTER(HostSeqs)]
+    L.seqs_free.argtypes = [C.POINTER(HostSeqs)]
+    L.host_rng_new.restype = C.c_void_p
+    L.host_rng_new.argtypes = [C.c_ulong]
+    L.model_bootstrap.restype = native.Model
+    L.model_bootstrap.argtypes = [C.c_void_p, native.Model]
+    return L
+
+
+def test_estimators_match_oracle(host):
+    rng = np.random.default_rng(3)
+    for trial in range(300):
+        scale = int(rng.choice([10, 1000, 100000, 2000000]))
+        diag = rng.integers(scale // 2, scale, size=4)
+        off = rng.integers(0, max(2, scale // rng.choice([10, 50, 1000])), size=12)
+        counts = np.zeros(16, np.uint32)
+        counts[[0, 5, 10, 15]] = diag
+        counts[[1, 2, 3, 4, 6, 7, 8, 9, 11, 12, 13, 14]] = off
+        m = native.Model((C.c_uint32 * 16)(*counts), int(counts.sum()) + 7)
+        om = oracle.Model((C.c_uint32 * 16)(*counts), int(counts.sum()) + 7)
+        for name, mid in native.MODELS.items():
+            got = host.model_estimate(C.byref(m), mid)
+            want = oracle.lib().orc_estimate(C.byref(om), mid)
+            assert (np.isnan(got) and np.isnan(want)) or got == pytest.approx(want, rel=1e-12, abs=0.0), (name, counts)
+        assert host.model_coverage(C.byref(m)) == oracle.lib().orc_model_coverage(C.byref(om))
+    tiny = native.Model((C.c_uint32 * 16)(1, 0, 1), 10)
+    assert np.isnan(host.model_estimate(C.byref(tiny), 0))  # src/model.c:87-89: nucl <= 3
+
+
+def test_fasta_reader_matches_fixture(host, tmp_path):
+    fa = gzip.open(G / "c1.fa.gz").read()
+    p = tmp_path / "c1.fa"
+    p.write_bytes(fa)
+    v = HostSeqs()
+    host.seqs_init(C.byref(v))
+    flags = C.c_int(0)
+    assert host.fasta_read(str(p).encode(), C.byref(v), C.byref(flags)) == 0
+    want = oracle.parse_fasta(fa)
+    assert v.size == len(want) == 2
+    for k, (name, seq) in enumerate(want):
+        assert v.data[k].name.decode() == name and v.data[k].len == len(seq)
+        assert C.string_at(v.data[k].S, v.data[k].len) == seq
+    assert flags.value == 0
+    host.seqs_free(C.byref(v))
+
+
+def test_fasta_normalises_and_joins(host, tmp_path):
+    p = tmp_path / "dir.with.dots" / "genome.v2.fasta"
+    p.parent.mkdir()
+    p.write_text(">c1 first contig\nacgtNNAC\nGT\n\n>c2\nTTTT-*\n>c3 x\nGGxG\n")
+    v = HostSeqs()
+    host.seqs_init(C.byref(v))
+    flags = C.c_int(0)
+    assert host.fasta_read(str(p).encode(), C.byref(v), C.byref(flags)) == 0
+    assert [C.string_at(v.data[k].S) for k in range(3)] == [b"ACGTACGT", b"TTTT", b"GGG"]
+    assert flags.value & 8  # HF_NON_ACGT
+    host.seqs_free(C.byref(v))
+    host.seqs_init(C.byref(v))
+    assert host.fasta_read_join(str(p).encode(), C.byref(v), C.byref(flags)) == 0
+    assert v.size == 1 and C.string_at(v.data[0].S) == b"ACGTACGT!TTTT!GGG"  # src/sequence.c:78-125
+    assert v.data[0].name == b"genome"  # src/io.c:176-186: basename up to the first dot
+    host.seqs_free(C.byref(v))
+
+
+def test_fasta_errors_are_soft(host, tmp_path):
+    for text in ("", "ACGT\n", ">\nACGT\n", ">name only"):
+        p = tmp_path / "bad.fa"
+        p.write_text(text)
+        v = HostSeqs()
+        host.seqs_init(C.byref(v))
+        flags = C.c_int(0)
+        assert host.fasta_read(str(p).encode(), C.byref(v), C.byref(flags)) == 1
+        assert flags.value & 256  # HF_SOFT_ERROR
+        host.seqs_free(C.byref(v))
+
+
+def test_bootstrap_is_a_multinomial_resample(host):
+    counts = [24436, 80, 94, 70, 83, 24432, 77, 85, 78, 87, 24406, 88, 84, 85, 81, 25720]
+    m = native.Model((C.c_uint32 * 16)(*counts), 100000)
+    rng = host.host_rng_new(42)
+    draws = np.array([list(host.model_bootstrap(rng, m).counts) for _ in range(400)], dtype=np.float64)
+    assert (draws.sum(axis=1) == sum(counts)).all()  # src/model.c:222-232: N is preserved
+    mean, want = draws.mean(axis=0), np.array(counts, dtype=np.float64)
+    assert np.all(np.abs(mean - want) < 5 * np.sqrt(want) / np.sqrt(400) + 1.0)
