@@ -51,7 +51,7 @@ struct andi_esa {
 	u64 *code = nullptr, *spec = nullptr;
 	u32 *SA = nullptr;
 	int32_t *LCP = nullptr;
-	u32 *dir = nullptr;
+	u64 *dir = nullptr;
 	PresenceLevels present{};
 	unsigned char *plen = nullptr;
 	int K = 0;
@@ -351,214 +351,7 @@ static int choose_depth(u32 N, u32 threshold) {
 	return k >= 2 ? k : 0;
 }
 
-struct SortScratch {
-	u64 *keys_a = nullptr, *keys_b = nullptr;
-	u32 *vals_a = nullptr, *vals_b = nullptr;
-	u32 *v = nullptr, *g = nullptr, *grp = nullptr, *rank = nullptr, *pos_a = nullptr, *pos_b = nullptr;
-	unsigned char *amb = nullptr;
-	u32 *d_count = nullptr;
-	void *tmp = nullptr;
-	size_t tmp_bytes = 0;
-};
-
-struct MaxOp {
-	__host__ __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a > b ? a : b; }
-};
-
-static int build_suffix_array(andi_ctx *ctx, andi_esa *E) {
-	const u32 N = E->N;
-	cudaStream_t st = ctx->stream;
-	SortScratch s;
-	CK(dalloc(ctx, &s.keys_a, N));
-	CK(dalloc(ctx, &s.keys_b, N));
-	CK(dalloc(ctx, &s.vals_a, N));
-	CK(dalloc(ctx, &s.v, N));
-	CK(dalloc(ctx, &s.g, N));
-	CK(dalloc(ctx, &s.grp, N));
-	CK(dalloc(ctx, &s.rank, N));
-	CK(dalloc(ctx, &s.pos_a, N));
-	CK(dalloc(ctx, &s.amb, N));
-	CK(dalloc(ctx, &s.d_count, 1));
-	// CUB temp: the largest of the three primitives at size N
-	size_t b1 = 0, b2 = 0, b3 = 0;
-	cub::DeviceRadixSort::SortPairs(nullptr, b1, s.keys_a, s.keys_b, s.vals_a, E->SA, (int)N, 0, 64, st);
-	cub::DeviceScan::InclusiveScan(nullptr, b2, s.v, s.g, MaxOp(), (int)N, st);
-	cub::DeviceSelect::Flagged(nullptr, b3, s.pos_a, s.amb, s.pos_a, s.d_count, (int)N, st);
-	s.tmp_bytes = std::max(b1, std::max(b2, b3));
-	CK(cudaMallocAsync(&s.tmp, s.tmp_bytes, st));
-
-	TextView rs = rs_view(E);
-	// round 0: 16 characters, 48-bit keys, straight into SA
-	k_suffix_keys<<<nblocks(N, 256), 256, 0, st>>>(rs, s.keys_a, s.vals_a);
-	size_t tb = s.tmp_bytes;
-	CK(cub::DeviceRadixSort::SortPairs(s.tmp, tb, s.keys_a, s.keys_b, s.vals_a, E->SA, (int)N, 0, 48, st));
-	k_head_values<<<nblocks(N, 256), 256, 0, st>>>(s.keys_b, N, nullptr, s.v);
-	tb = s.tmp_bytes;
-	CK(cub::DeviceScan::InclusiveScan(s.tmp, tb, s.v, s.g, MaxOp(), (int)N, st));
-	k_apply_groups<<<nblocks(N, 256), 256, 0, st>>>(s.g, N, nullptr, E->SA, E->SA, s.grp, s.rank, s.amb);
-	k_iota<<<nblocks(N, 256), 256, 0, st>>>(s.v, N);
-	tb = s.tmp_bytes;
-	CK(cub::DeviceSelect::Flagged(s.tmp, tb, s.v, s.amb, s.pos_a, s.d_count, (int)N, st));
-	ctx->st.esa_launches += 4;
-	ctx->st.cub_calls += 3;
-	u32 m = 0;
-	CK(cudaMemcpyAsync(&m, s.d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
-
-	if (m) {
-		CK(dalloc(ctx, &s.vals_b, m));
-		CK(dalloc(ctx, &s.pos_b, m));
-	}
-	for (u32 h = 16; m > 0; h *= 2) {
-		int bits = 33;
-		while (bits < 64 && (1ULL << (bits - 32)) <= (u64)N) bits++;  // group index needs log2(N) bits
-		k_round_keys<<<nblocks(m, 256), 256, 0, st>>>(s.pos_a, m, E->SA, s.grp, s.rank, h, N, s.keys_a, s.vals_a);
-		tb = s.tmp_bytes;
-		CK(cub::DeviceRadixSort::SortPairs(s.tmp, tb, s.keys_a, s.keys_b, s.vals_a, s.vals_b, (int)m, 0, bits, st));
-		k_head_values<<<nblocks(m, 256), 256, 0, st>>>(s.keys_b, m, s.pos_a, s.v);
-		tb = s.tmp_bytes;
-		CK(cub::DeviceScan::InclusiveScan(s.tmp, tb, s.v, s.g, MaxOp(), (int)m, st));
-		k_apply_groups<<<nblocks(m, 256), 256, 0, st>>>(s.g, m, s.pos_a, s.vals_b, E->SA, s.grp, s.rank, s.amb);
-		tb = s.tmp_bytes;
-		CK(cub::DeviceSelect::Flagged(s.tmp, tb, s.pos_a, s.amb, s.pos_b, s.d_count, (int)m, st));
-		ctx->st.esa_launches += 3;
-		ctx->st.cub_calls += 3;
-		ctx->st.sa_rounds++;
-		CK(cudaMemcpyAsync(&m, s.d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		std::swap(s.pos_a, s.pos_b);
-		if (h > N) break;
-	}
-	dfree(ctx, s.keys_a), dfree(ctx, s.keys_b), dfree(ctx, s.vals_a), dfree(ctx, s.vals_b);
-	dfree(ctx, s.v), dfree(ctx, s.g), dfree(ctx, s.grp), dfree(ctx, s.rank);
-	dfree(ctx, s.pos_a), dfree(ctx, s.pos_b), dfree(ctx, s.amb), dfree(ctx, s.d_count);
-	cudaFreeAsync(s.tmp, st);
-	return ANDI_OK;
-}
-
-static int build_lcp(andi_ctx *ctx, andi_esa *E) {
-	const u32 N = E->N;
-	cudaStream_t st = ctx->stream;
-	int32_t *phi = nullptr;
-	CK(dalloc(ctx, &phi, N));
-	TextView rs = rs_view(E);
-	k_phi<<<nblocks(N, 256), 256, 0, st>>>(E->SA, N, phi);
-	u32 slices = (N + 31) / 32;
-	if (E->has_sep)
-		k_plcp<true><<<nblocks(slices, 128), 128, 0, st>>>(rs, phi);
-	else
-		k_plcp<false><<<nblocks(slices, 128), 128, 0, st>>>(rs, phi);
-	k_lcp_from_plcp<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(E->SA, phi, N, E->LCP);
-	ctx->st.esa_launches += 3;
-	dfree(ctx, phi);
-	return ANDI_OK;
-}
-
-static int build_directory(andi_ctx *ctx, andi_esa *E) {
-	cudaStream_t st = ctx->stream;
-	const int K = E->K;
-	if (K == 0) return ANDI_OK;
-	const size_t entries = ((size_t)1 << (2 * K)) + 1;
-	CK(dalloc(ctx, &E->dir, entries));
-	TextView rs = rs_view(E);
-	k_fill_u32<<<std::min<unsigned>(nblocks(entries, 256), 4096u), 256, 0, st>>>(E->dir, entries, E->N);
-	if (E->has_sep)
-		k_dir_heads<true><<<nblocks(E->N, 256), 256, 0, st>>>(rs, E->SA, K, E->dir);
-	else
-		k_dir_heads<false><<<nblocks(E->N, 256), 256, 0, st>>>(rs, E->SA, K, E->dir);
-	// presence bitmaps, levels 1 .. K-1
-	size_t words = 0;
-	for (int m = 1; m < K; m++) {
-		E->present.offset[m] = (u32)words;
-		words += (((size_t)1 << (2 * m)) + 31) / 32;
-	}
-	CK(dalloc(ctx, &E->present.bits, words));
-	u32 top_bits = 1u << (2 * (K - 1));
-	k_presence_from_dir<<<nblocks((top_bits + 31) / 32, 256), 256, 0, st>>>(E->dir, top_bits,
-																			 E->present.bits + E->present.offset[K - 1]);
-	for (int m = K - 2; m >= 1; m--) {
-		u32 nb = 1u << (2 * m);
-		k_presence_down<<<nblocks((nb + 31) / 32, 256), 256, 0, st>>>(E->present.bits + E->present.offset[m + 1], nb,
-																	   E->present.bits + E->present.offset[m]);
-	}
-	k_presence_patch<<<nblocks(E->N, 256), 256, 0, st>>>(rs, K, E->present);
-	CK(dalloc(ctx, &E->plen, entries - 1));
-	k_prefix_len<<<nblocks(entries - 1, 256), 256, 0, st>>>(E->present, K, E->plen);
-	dfree(ctx, E->present.bits);  // only the table is needed from here on
-	ctx->st.esa_launches += 4 + (K - 1);
-	return ANDI_OK;
-}
-
-static int build_full(andi_ctx *ctx, andi_esa *E) {
-	// CLD, FVC, prefix cache: only for the reference-visible esa_s (ANDI_ESA_FULL)
-	cudaStream_t st = ctx->stream;
-	const u32 N = E->N;
-	CK(dalloc(ctx, &E->CLD, (size_t)N + 1));
-	CK(dalloc(ctx, &E->FVC, (size_t)N));
-	CK(dalloc(ctx, &E->cache, (size_t)1 << 20));
-	TextView rs = rs_view(E);
-	k_fvc<<<nblocks(N, 256), 256, 0, st>>>(rs, E->SA, E->LCP, E->FVC);
-	MinPyramid P{};
-	P.level[0] = E->LCP;
-	P.size[0] = N + 1;
-	P.levels = 1;
-	std::vector<int32_t *> owned;
-	while (P.size[P.levels - 1] > 32) {
-		u32 ns = (P.size[P.levels - 1] + 31) / 32;
-		int32_t *buf = nullptr;
-		CK(dalloc(ctx, &buf, ns));
-		owned.push_back(buf);
-		k_min_reduce32<<<nblocks(ns, 256), 256, 0, st>>>(P.level[P.levels - 1], P.size[P.levels - 1], buf, ns);
-		P.level[P.levels] = buf;
-		P.size[P.levels] = ns;
-		P.levels++;
-		ctx->st.esa_launches++;
-	}
-	k_cld<<<nblocks(N, 256), 256, 0, st>>>(P, N, E->CLD);
-	for (auto b : owned) cudaFreeAsync(b, st);
-	EsaView V;
-	V.rs = rs, V.SA = E->SA, V.LCP = E->LCP, V.CLD = E->CLD, V.FVC = E->FVC;
-	k_prefix_cache<<<nblocks(1u << 20, 128), 128, 0, st>>>(V, E->cache);
-	ctx->st.esa_launches += 3;
-	E->full = true;
-	return ANDI_OK;
-}
-
-static void esa_release(andi_esa *E) {
-	andi_ctx *ctx = E->ctx;
-	dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->SA), dfree(ctx, E->LCP);
-	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->plen), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
-	dfree(ctx, E->cache);
-}
-
-// RS planes are in place; build everything else.
-static int build_index(andi_ctx *ctx, andi_esa *E, unsigned flags) {
-	cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
-	mark(ctx, e0);
-	if (!ctx->first_ev) {
-		ctx->first_ev = get_event(ctx);
-		mark(ctx, ctx->first_ev);
-	}
-	CK(dalloc(ctx, &E->SA, E->N));
-	CK(dalloc(ctx, &E->LCP, (size_t)E->N + 1));
-	int rc = build_suffix_array(ctx, E);
-	if (!rc) rc = build_lcp(ctx, E);
-	if (!rc) rc = build_directory(ctx, E);
-	if (!rc && (flags & ANDI_ESA_FULL)) rc = build_full(ctx, E);
-	mark(ctx, e1);
-	ctx->esa_ev.emplace_back(e0, e1);
-	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);
-	mark(ctx, ctx->last_ev);
-	ctx->st.subjects++;
-	if (!rc) {
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess) {
-			ctx->err = std::string("index kernels: ") + cudaGetErrorString(e);
-			rc = ANDI_ERR_CUDA;
-		}
-	}
-	return rc;
-}
+#include "index_host.cuh"
 
 extern "C" int andi_esa_build(andi_ctx *ctx, size_t subject, unsigned flags, andi_esa **out) {
 	if (!ctx || !out || subject >= ctx->n) return ANDI_ERR_ARG;

@@ -175,17 +175,6 @@ __global__ void k_round_keys(const u32 *__restrict__ pos, u32 m, const u32 *__re
 	vals[k] = sfx;
 }
 
-__global__ void k_iota(u32 *a, u32 n) {
-	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) a[i] = i;
-}
-
-__global__ void k_fill_u32(u32 *a, size_t n, u32 v) {
-	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	size_t stride = (size_t)gridDim.x * blockDim.x;
-	for (; i < n; i += stride) a[i] = v;
-}
-
 // ------------------------------------------------------------------ E2: LCP
 // src/esa.c:373-426. phi[SA[j]] = SA[j-1]; PLCP in text order with the l-1 carry-over, each
 // thread owning a slice of 32 consecutive text positions (the carry restarts at 0 at a slice
@@ -238,56 +227,23 @@ __global__ void k_lcp_from_plcp(const u32 *__restrict__ SA, const int32_t *__res
 
 // ------------------------------------------------------------------ k-mer directory
 // Not in the reference: the device-side replacement for its 4^10 prefix cache + child-table
-// descent. dir[x] = first SA index whose suffix starts with a k-mer >= x (k nucleotides, no
-// separator, inside the text); dir[4^k] = N. All suffixes sharing a k-mer form one SA range
-// starting at dir[key]; dir[key+1] bounds it from above (the few suffixes with a separator
-// in their first k characters that sort in between are tolerated by the scan, which compares
-// from character 0).
-
-template <bool SPEC>
-__device__ __forceinline__ bool suffix_kmer(const TextView &rs, u32 p, int K, u32 &key) {
-	if (p + (u32)K > rs.len) return false;
-	if (SPEC) {
-		u64 sw = window32(rs.spec, p);
-		u64 mask = (K >= 32) ? ~0ULL : ((1ULL << (2 * K)) - 1ULL);
-		if (sw & mask) return false;
-	} else {
-		if (p <= rs.mid && rs.mid < p + (u32)K) return false;
-	}
-	key = kmer_key(window32(rs.code, p), K);
-	return true;
-}
-
-template <bool SPEC>
-__global__ void k_dir_heads(TextView rs, const u32 *__restrict__ SA, int K, u32 *__restrict__ dir) {
-	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= rs.len) return;
-	u32 key;
-	if (!suffix_kmer<SPEC>(rs, SA[j], K, key)) return;
-	// nearest earlier suffix with a valid k-mer
-	long long prev = -1;
-	for (long long b = (long long)j - 1; b >= 0; b--) {
-		u32 pk;
-		if (suffix_kmer<SPEC>(rs, SA[b], K, pk)) {
-			prev = (long long)pk;
-			break;
-		}
-	}
-	if (prev == (long long)key) return;
-	for (long long x = prev + 1; x <= (long long)key; x++) dir[x] = j;
-}
-
-// Presence bitmaps: level m (1 <= m < K) has bit x set iff the m-mer x occurs in RS.
-// Level K-1 comes from the directory, lower levels by OR-ing groups of four bits, and
-// suffixes that hit a separator / the end before K characters are patched in.
-__global__ void k_presence_from_dir(const u32 *__restrict__ dir, u32 nbits, u32 *__restrict__ bits) {
+// descent. dir[x] (written by k_bucket_sort, sa_bucket.cuh) = first SA index of the suffixes
+// that start with the k-mer x (k nucleotides, no separator, inside the text) | their number
+// << 32; they are contiguous in SA.
+//
+// Presence bitmaps: level m (1 <= m < K) has bit x set iff the m-mer x occurs in RS. Level K-1
+// comes from the directory counts, lower levels by OR-ing groups of four bits, and suffixes
+// that hit a separator / the end before K characters are patched in. They only serve to
+// build the prefix-length table (k_prefix_len) and are freed afterwards.
+__global__ void k_presence_from_dir(const u64 *__restrict__ dir, u32 nbits, u32 *__restrict__ bits) {
 	u32 w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w * 32u >= nbits) return;
 	u32 out = 0;
 	for (u32 b = 0; b < 32; b++) {
 		u32 x = w * 32u + b;
 		if (x >= nbits) break;
-		if (dir[4u * x + 4u] > dir[4u * x]) out |= 1u << b;
+		u64 any = (dir[4u * x] | dir[4u * x + 1] | dir[4u * x + 2] | dir[4u * x + 3]) >> 32;
+		if (any) out |= 1u << b;
 	}
 	bits[w] = out;
 }

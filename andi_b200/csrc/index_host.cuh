@@ -1,0 +1,302 @@
+// andi_b200/csrc/index_host.cuh -- host side of index construction (esa_init, src/esa.c:254-277);
+// included by andi_b200.cu.
+//
+// Optimistic pipeline, ONE host synchronisation per subject in the common case:
+//   bucket suffix sort (sa_bucket.cuh) -> direct LCP -> k-mer directory / presence / prefix
+//   lengths -> read back two flags {tied suffixes, LCP overflow}.
+// Only when suffixes are still tied (repeats longer than ANDI_SORT_CAP, oversized buckets) do
+// the prefix-doubling rounds run (group, rank[i+h]) with h = K, 2K, ...; only when an LCP value
+// reached the direct cap is the LCP recomputed through the phi array (src/esa.c:373-426).
+// The radix sort / scan / select used by the doubling rounds are CUB device primitives.
+#pragma once
+#include "sa_bucket.cuh"
+
+#include <thrust/iterator/counting_iterator.h>
+
+#define ANDI_LCP_DIRECT_CAP 1024u
+
+struct MaxOp {
+	__host__ __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a > b ? a : b; }
+};
+
+// Refine the suffixes flagged in amb[0..N) (grp / rank hold their current groups, all of depth
+// >= h0) until every group is a singleton.
+static int doubling_rounds(andi_ctx *ctx, andi_esa *E, u32 *grp, u32 *rank, unsigned char *amb, u32 h0) {
+	const u32 N = E->N;
+	cudaStream_t st = ctx->stream;
+	u32 *pos_a = nullptr, *pos_b = nullptr, *d_count = nullptr;
+	CK(dalloc(ctx, &pos_a, N));
+	CK(dalloc(ctx, &d_count, 1));
+	size_t sel_bytes = 0;
+	thrust::counting_iterator<u32> iota(0);
+	cub::DeviceSelect::Flagged(nullptr, sel_bytes, iota, amb, pos_a, d_count, (int)N, st);
+	void *tmp = nullptr;
+	CK(cudaMallocAsync(&tmp, sel_bytes, st));
+	CK(cub::DeviceSelect::Flagged(tmp, sel_bytes, iota, amb, pos_a, d_count, (int)N, st));
+	ctx->st.cub_calls++;
+	u32 m = 0;
+	CK(cudaMemcpyAsync(&m, d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	cudaFreeAsync(tmp, st);
+	if (m == 0) {
+		dfree(ctx, pos_a), dfree(ctx, d_count);
+		return ANDI_OK;
+	}
+	u64 *keys_a = nullptr, *keys_b = nullptr;
+	u32 *vals_a = nullptr, *vals_b = nullptr, *v = nullptr, *g = nullptr;
+	unsigned char *amb2 = nullptr;
+	CK(dalloc(ctx, &keys_a, m));
+	CK(dalloc(ctx, &keys_b, m));
+	CK(dalloc(ctx, &vals_a, m));
+	CK(dalloc(ctx, &vals_b, m));
+	CK(dalloc(ctx, &v, m));
+	CK(dalloc(ctx, &g, m));
+	CK(dalloc(ctx, &amb2, m));
+	CK(dalloc(ctx, &pos_b, m));
+	size_t b1 = 0, b2 = 0, b3 = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, b1, keys_a, keys_b, vals_a, vals_b, (int)m, 0, 64, st);
+	cub::DeviceScan::InclusiveScan(nullptr, b2, v, g, MaxOp(), (int)m, st);
+	cub::DeviceSelect::Flagged(nullptr, b3, pos_a, amb2, pos_b, d_count, (int)m, st);
+	size_t tmp_bytes = std::max(b1, std::max(b2, b3));
+	CK(cudaMallocAsync(&tmp, tmp_bytes, st));
+	int bits = 33;
+	while (bits < 64 && (1ULL << (bits - 32)) <= (u64)N) bits++;  // the group index needs log2(N) bits
+	for (u32 h = h0; m > 0; h *= 2) {
+		size_t tb = tmp_bytes;
+		k_round_keys<<<nblocks(m, 256), 256, 0, st>>>(pos_a, m, E->SA, grp, rank, h, N, keys_a, vals_a);
+		CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys_a, keys_b, vals_a, vals_b, (int)m, 0, bits, st));
+		k_head_values<<<nblocks(m, 256), 256, 0, st>>>(keys_b, m, pos_a, v);
+		tb = tmp_bytes;
+		CK(cub::DeviceScan::InclusiveScan(tmp, tb, v, g, MaxOp(), (int)m, st));
+		k_apply_groups<<<nblocks(m, 256), 256, 0, st>>>(g, m, pos_a, vals_b, E->SA, grp, rank, amb2);
+		tb = tmp_bytes;
+		CK(cub::DeviceSelect::Flagged(tmp, tb, pos_a, amb2, pos_b, d_count, (int)m, st));
+		ctx->st.esa_launches += 3;
+		ctx->st.cub_calls += 3;
+		ctx->st.sa_rounds++;
+		CK(cudaMemcpyAsync(&m, d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		std::swap(pos_a, pos_b);
+		if (h > N) break;
+	}
+	dfree(ctx, keys_a), dfree(ctx, keys_b), dfree(ctx, vals_a), dfree(ctx, vals_b);
+	dfree(ctx, v), dfree(ctx, g), dfree(ctx, amb2), dfree(ctx, pos_a), dfree(ctx, pos_b), dfree(ctx, d_count);
+	cudaFreeAsync(tmp, st);
+	return ANDI_OK;
+}
+
+// Fallback sorter for indexes without a directory (K == 0: tiny thresholds): LSD radix sort
+// on the first 16 characters (48-bit keys), then doubling from h = 16.
+static int build_sa_radix(andi_ctx *ctx, andi_esa *E) {
+	const u32 N = E->N;
+	cudaStream_t st = ctx->stream;
+	u64 *keys_a = nullptr, *keys_b = nullptr;
+	u32 *vals_a = nullptr, *v = nullptr, *g = nullptr, *grp = nullptr, *rank = nullptr;
+	unsigned char *amb = nullptr;
+	CK(dalloc(ctx, &keys_a, N));
+	CK(dalloc(ctx, &keys_b, N));
+	CK(dalloc(ctx, &vals_a, N));
+	CK(dalloc(ctx, &v, N));
+	CK(dalloc(ctx, &g, N));
+	CK(dalloc(ctx, &grp, N));
+	CK(dalloc(ctx, &rank, N));
+	CK(dalloc(ctx, &amb, N));
+	size_t b1 = 0, b2 = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, b1, keys_a, keys_b, vals_a, E->SA, (int)N, 0, 48, st);
+	cub::DeviceScan::InclusiveScan(nullptr, b2, v, g, MaxOp(), (int)N, st);
+	size_t tmp_bytes = std::max(b1, b2);
+	void *tmp = nullptr;
+	CK(cudaMallocAsync(&tmp, tmp_bytes, st));
+	TextView rs = rs_view(E);
+	k_suffix_keys<<<nblocks(N, 256), 256, 0, st>>>(rs, keys_a, vals_a);
+	size_t tb = tmp_bytes;
+	CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys_a, keys_b, vals_a, E->SA, (int)N, 0, 48, st));
+	k_head_values<<<nblocks(N, 256), 256, 0, st>>>(keys_b, N, nullptr, v);
+	tb = tmp_bytes;
+	CK(cub::DeviceScan::InclusiveScan(tmp, tb, v, g, MaxOp(), (int)N, st));
+	k_apply_groups<<<nblocks(N, 256), 256, 0, st>>>(g, N, nullptr, E->SA, E->SA, grp, rank, amb);
+	ctx->st.esa_launches += 3;
+	ctx->st.cub_calls += 2;
+	dfree(ctx, keys_a), dfree(ctx, keys_b), dfree(ctx, vals_a), dfree(ctx, v), dfree(ctx, g);
+	cudaFreeAsync(tmp, st);
+	int rc = doubling_rounds(ctx, E, grp, rank, amb, 16);
+	dfree(ctx, grp), dfree(ctx, rank), dfree(ctx, amb);
+	return rc;
+}
+
+// src/esa.c:373-426 in full: phi array, blocked Kasai, permute.
+static int build_lcp_phi(andi_ctx *ctx, andi_esa *E) {
+	const u32 N = E->N;
+	cudaStream_t st = ctx->stream;
+	int32_t *phi = nullptr;
+	CK(dalloc(ctx, &phi, N));
+	TextView rs = rs_view(E);
+	k_phi<<<nblocks(N, 256), 256, 0, st>>>(E->SA, N, phi);
+	u32 slices = (N + 31) / 32;
+	if (E->has_sep)
+		k_plcp<true><<<nblocks(slices, 128), 128, 0, st>>>(rs, phi);
+	else
+		k_plcp<false><<<nblocks(slices, 128), 128, 0, st>>>(rs, phi);
+	k_lcp_from_plcp<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(E->SA, phi, N, E->LCP);
+	ctx->st.esa_launches += 3;
+	dfree(ctx, phi);
+	return ANDI_OK;
+}
+
+// Presence bitmaps (levels 1..K-1) from the directory counts, then the prefix-length table.
+static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
+	cudaStream_t st = ctx->stream;
+	const int K = E->K;
+	const size_t kmers = (size_t)1 << (2 * K);
+	TextView rs = rs_view(E);
+	size_t words = 0;
+	for (int m = 1; m < K; m++) {
+		E->present.offset[m] = (u32)words;
+		words += (((size_t)1 << (2 * m)) + 31) / 32;
+	}
+	CK(dalloc(ctx, &E->present.bits, words));
+	u32 top_bits = 1u << (2 * (K - 1));
+	k_presence_from_dir<<<nblocks((top_bits + 31) / 32, 256), 256, 0, st>>>(E->dir, top_bits,
+																			 E->present.bits + E->present.offset[K - 1]);
+	for (int m = K - 2; m >= 1; m--) {
+		u32 nb = 1u << (2 * m);
+		k_presence_down<<<nblocks((nb + 31) / 32, 256), 256, 0, st>>>(E->present.bits + E->present.offset[m + 1], nb,
+																	   E->present.bits + E->present.offset[m]);
+	}
+	k_presence_patch<<<nblocks(E->N, 256), 256, 0, st>>>(rs, K, E->present);
+	CK(dalloc(ctx, &E->plen, kmers));
+	k_prefix_len<<<nblocks(kmers, 256), 256, 0, st>>>(E->present, K, E->plen);
+	dfree(ctx, E->present.bits);  // only the table is needed from here on
+	ctx->st.esa_launches += 3 + (K - 1);
+	return ANDI_OK;
+}
+
+static int build_full(andi_ctx *ctx, andi_esa *E) {
+	// CLD, FVC, prefix cache: only for the reference-visible esa_s (ANDI_ESA_FULL)
+	cudaStream_t st = ctx->stream;
+	const u32 N = E->N;
+	CK(dalloc(ctx, &E->CLD, (size_t)N + 1));
+	CK(dalloc(ctx, &E->FVC, (size_t)N));
+	CK(dalloc(ctx, &E->cache, (size_t)1 << 20));
+	TextView rs = rs_view(E);
+	k_fvc<<<nblocks(N, 256), 256, 0, st>>>(rs, E->SA, E->LCP, E->FVC);
+	MinPyramid P{};
+	P.level[0] = E->LCP;
+	P.size[0] = N + 1;
+	P.levels = 1;
+	std::vector<int32_t *> owned;
+	while (P.size[P.levels - 1] > 32) {
+		u32 ns = (P.size[P.levels - 1] + 31) / 32;
+		int32_t *buf = nullptr;
+		CK(dalloc(ctx, &buf, ns));
+		owned.push_back(buf);
+		k_min_reduce32<<<nblocks(ns, 256), 256, 0, st>>>(P.level[P.levels - 1], P.size[P.levels - 1], buf, ns);
+		P.level[P.levels] = buf;
+		P.size[P.levels] = ns;
+		P.levels++;
+		ctx->st.esa_launches++;
+	}
+	k_cld<<<nblocks(N, 256), 256, 0, st>>>(P, N, E->CLD);
+	for (auto b : owned) cudaFreeAsync(b, st);
+	EsaView V;
+	V.rs = rs, V.SA = E->SA, V.LCP = E->LCP, V.CLD = E->CLD, V.FVC = E->FVC;
+	k_prefix_cache<<<nblocks(1u << 20, 128), 128, 0, st>>>(V, E->cache);
+	ctx->st.esa_launches += 3;
+	E->full = true;
+	return ANDI_OK;
+}
+
+static void esa_release(andi_esa *E) {
+	andi_ctx *ctx = E->ctx;
+	dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->SA), dfree(ctx, E->LCP);
+	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->plen), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
+	dfree(ctx, E->cache);
+}
+
+static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
+	const u32 N = E->N;
+	const int K = E->K;
+	cudaStream_t st = ctx->stream;
+	const size_t kmers = (size_t)1 << (2 * K);
+	TextView rs = rs_view(E);
+	u32 *hist = nullptr, *bstart = nullptr, *cursor = nullptr, *grp = nullptr, *rank = nullptr, *flags = nullptr;
+	unsigned char *amb = nullptr;
+	CK(dalloc(ctx, &hist, kmers + 1));
+	CK(dalloc(ctx, &bstart, kmers + 1));
+	CK(dalloc(ctx, &cursor, kmers));
+	CK(dalloc(ctx, &grp, N));
+	CK(dalloc(ctx, &rank, N));
+	CK(dalloc(ctx, &amb, N));
+	CK(dalloc(ctx, &flags, 2));
+	CK(dalloc(ctx, &E->dir, kmers));
+	CK(cudaMemsetAsync(hist, 0, (kmers + 1) * sizeof(u32), st));
+	CK(cudaMemsetAsync(cursor, 0, kmers * sizeof(u32), st));
+	CK(cudaMemsetAsync(flags, 0, 2 * sizeof(u32), st));
+	size_t scan_bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, hist, bstart, (int)(kmers + 1), st);
+	void *tmp = nullptr;
+	CK(cudaMallocAsync(&tmp, scan_bytes, st));
+	k_bucket_hist<<<nblocks(N, 256), 256, 0, st>>>(rs, K, hist);
+	CK(cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, hist, bstart, (int)(kmers + 1), st));
+	k_bucket_scatter<<<nblocks(N, 256), 256, 0, st>>>(rs, K, bstart, cursor, E->SA);
+	k_bucket_sort<<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, bstart, E->SA, grp, rank, amb, E->dir, flags);
+	k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, flags + 1);
+	ctx->st.esa_launches += 4;
+	ctx->st.cub_calls += 1;
+	cudaFreeAsync(tmp, st);
+	dfree(ctx, hist), dfree(ctx, cursor);
+	int rc = build_prefix_lengths(ctx, E);
+	u32 h_flags[2] = {0, 0};
+	if (!rc) {
+		CK(cudaMemcpyAsync(h_flags, flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	if (!rc && h_flags[0]) {
+		// tied suffixes: refine them, then the LCP has to be taken again
+		rc = doubling_rounds(ctx, E, grp, rank, amb, (u32)K);
+		if (!rc) {
+			CK(cudaMemsetAsync(flags + 1, 0, sizeof(u32), st));
+			k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, flags + 1);
+			ctx->st.esa_launches++;
+			CK(cudaMemcpyAsync(h_flags, flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+		}
+	}
+	if (!rc && h_flags[1]) rc = build_lcp_phi(ctx, E);
+	dfree(ctx, bstart), dfree(ctx, grp), dfree(ctx, rank), dfree(ctx, amb), dfree(ctx, flags);
+	return rc;
+}
+
+// RS planes are in place; build everything else.
+static int build_index(andi_ctx *ctx, andi_esa *E, unsigned flags) {
+	cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+	mark(ctx, e0);
+	if (!ctx->first_ev) {
+		ctx->first_ev = get_event(ctx);
+		mark(ctx, ctx->first_ev);
+	}
+	CK(dalloc(ctx, &E->SA, E->N));
+	CK(dalloc(ctx, &E->LCP, (size_t)E->N + 1));
+	int rc;
+	if (E->K >= 2) {
+		rc = build_index_bucket(ctx, E);
+	} else {
+		rc = build_sa_radix(ctx, E);
+		if (!rc) rc = build_lcp_phi(ctx, E);
+	}
+	if (!rc && (flags & ANDI_ESA_FULL)) rc = build_full(ctx, E);
+	mark(ctx, e1);
+	ctx->esa_ev.emplace_back(e0, e1);
+	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);
+	mark(ctx, ctx->last_ev);
+	ctx->st.subjects++;
+	if (!rc) {
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) {
+			ctx->err = std::string("index kernels: ") + cudaGetErrorString(e);
+			rc = ANDI_ERR_CUDA;
+		}
+	}
+	return rc;
+}
+

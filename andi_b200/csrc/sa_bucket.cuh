@@ -1,0 +1,139 @@
+// andi_b200/csrc/sa_bucket.cuh -- suffix array by k-mer bucketing, the fast
+// front end of the index build. Stands where src/esa.c:303 calls divsufsort.
+//
+//   k_bucket_hist     count suffixes per k-mer bucket (atomics on an L2-resident table)
+//   (exclusive scan)  bucket starts
+//   k_bucket_scatter  drop every suffix into its bucket
+//   k_bucket_sort     one thread per bucket: order its (usually 1-3) suffixes by direct
+//                     comparison of the packed text, at most ANDI_SORT_CAP characters deep,
+//                     and emit what the rest of the build needs: group ids / ranks for the
+//                     doubling rounds, the k-mer directory entry of the walk, presence bits
+//
+// Suffixes that are still tied afterwards (repeats longer than the cap, buckets larger than
+// ANDI_SORT_MAX) are finished by the prefix-doubling rounds of andi_b200.cu starting at h = K;
+// genome-like text without long repeats needs none.
+//
+// Bucket key of a suffix = its first K characters as 2-bit codes, with everything from the
+// first separator / the text end onwards replaced by 'A' (0). The reference's byte order puts
+// every separator below 'A', so this key is monotone in suffix order; the suffixes that were
+// padded sort to the front of their bucket by the full comparison.
+#pragma once
+#include "text.cuh"
+
+#define ANDI_SORT_MAX 16   // buckets up to this size are sorted by one thread
+#define ANDI_SORT_CAP 128  // characters compared before two suffixes are declared tied
+
+// Number of leading nucleotides of the suffix at p (capped at 32) and its padded key.
+__device__ __forceinline__ u32 padded_key(const TextView &rs, u32 p, int K, u32 &run) {
+	u64 sw = window32(rs.spec, p);
+	u32 r = sw ? (u32)(__ffsll((long long)sw) - 1) >> 1 : 32u;
+	r = min(r, rs.len - p);
+	run = r;
+	u64 cw = window32(rs.code, p);
+	if (r < 32u) cw &= (1ULL << (2u * r)) - 1ULL;
+	return kmer_key(cw, K);
+}
+
+__global__ void k_bucket_hist(TextView rs, int K, u32 *__restrict__ hist) {
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= rs.len) return;
+	u32 run;
+	atomicAdd(hist + padded_key(rs, i, K, run), 1u);
+}
+
+__global__ void k_bucket_scatter(TextView rs, int K, const u32 *__restrict__ bstart, u32 *__restrict__ cursor,
+								 u32 *__restrict__ SA) {
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= rs.len) return;
+	u32 run;
+	u32 key = padded_key(rs, i, K, run);
+	SA[bstart[key] + atomicAdd(cursor + key, 1u)] = i;
+}
+
+// Compare suffixes a != b of RS in the reference's byte order, looking at most `cap`
+// characters deep. Returns <0, >0, or 0 when they agree on the first `cap` characters.
+__device__ __forceinline__ int compare_suffixes(const TextView &rs, u32 a, u32 b, u32 cap) {
+	u32 lim = min(cap, rs.len - max(a, b));
+	u32 m = match_len<true>(rs, a, rs, b, lim);
+	if (m == cap) return 0;
+	u32 sa = sym3<true>(rs, a + m), sb = sym3<true>(rs, b + m);
+	return sa < sb ? -1 : 1;  // different suffixes always differ here (end of text ranks lowest)
+}
+
+// dir64[key] = first SA index of the suffixes that really start with this k-mer (no
+// separator inside) | their number << 32.
+__global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, u32 *__restrict__ SA,
+							  u32 *__restrict__ grp, u32 *__restrict__ rank, unsigned char *__restrict__ amb,
+							  u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous) {
+	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
+	if (key >= (1u << (2 * K))) return;
+	const u32 b = bstart[key], e = bstart[key + 1], s = e - b;
+	if (s == 0) {
+		dir64[key] = (u64)e;
+		return;
+	}
+	u32 valid = 0;
+	if (s > ANDI_SORT_MAX) {
+		// left to the doubling rounds as one group of depth K
+		for (u32 j = b; j < e; j++) {
+			u32 p = SA[j], run;
+			padded_key(rs, p, K, run);
+			valid += run >= (u32)K;
+			grp[j] = b, rank[p] = b, amb[j] = 1;
+		}
+		atomicAdd(n_ambiguous, s);
+		dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
+		return;
+	}
+	u32 v[ANDI_SORT_MAX];
+#pragma unroll
+	for (int x = 0; x < ANDI_SORT_MAX; x++) v[x] = x < (int)s ? SA[b + x] : 0u;
+	// insertion sort; ties (equal up to the cap) keep their relative order
+	for (u32 x = 1; x < s; x++) {
+		u32 cur = v[x];
+		u32 y = x;
+		while (y > 0 && compare_suffixes(rs, v[y - 1], cur, ANDI_SORT_CAP) > 0) {
+			v[y] = v[y - 1];
+			y--;
+		}
+		v[y] = cur;
+	}
+	// tie bit x: v[x] agrees with v[x-1] on the first ANDI_SORT_CAP characters
+	u32 ties = 0;
+	for (u32 x = 1; x < s; x++)
+		if (compare_suffixes(rs, v[x - 1], v[x], ANDI_SORT_CAP) == 0) ties |= 1u << x;
+	u32 head = b, tied = 0;
+	for (u32 x = 0; x < s; x++) {
+		u32 p = v[x], run;
+		padded_key(rs, p, K, run);
+		valid += run >= (u32)K;
+		bool same = (ties >> x) & 1u;
+		if (!same) head = b + x;
+		SA[b + x] = p;
+		grp[b + x] = head;
+		rank[p] = head;
+		bool a = same || ((ties >> (x + 1)) & 1u);
+		amb[b + x] = a;
+		tied += a;
+	}
+	if (tied) atomicAdd(n_ambiguous, tied);
+	dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
+}
+
+// LCP[j] = lcp(SA[j-1], SA[j]) by direct comparison, at most `cap` characters; pairs that reach
+// the cap raise *overflow and the caller recomputes everything through the phi array
+// (src/esa.c:373-426, k_phi / k_plcp) -- only repeat-rich texts get there.
+__global__ void k_lcp_direct(TextView rs, const u32 *__restrict__ SA, u32 cap, int32_t *__restrict__ LCP,
+							 u32 *__restrict__ overflow) {
+	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j > rs.len) return;
+	if (j == 0 || j == rs.len) {
+		LCP[j] = -1;
+		return;
+	}
+	u32 a = SA[j - 1], b = SA[j];
+	u32 lim = min(cap, rs.len - max(a, b));
+	u32 m = match_len<true>(rs, a, rs, b, lim);
+	if (m == cap) atomicExch(overflow, 1u);
+	LCP[j] = (int32_t)m;
+}

@@ -247,7 +247,8 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ DIR
 		if (op == OP_DIR) {
-			u32 t0 = __ldg(S.dir + L.key), t1 = __ldg(S.dir + L.key + 1);
+			u64 de = __ldg(S.dir + L.key);
+			u32 t0 = (u32)de, t1 = t0 + (u32)(de >> 32);
 			L.short_len = __ldg(S.plen + L.key);  // the answer if the k-mer turns out to be absent
 			if (t1 > t0) {
 				if (t1 - t0 <= ANDI_SCAN_MAX) {
@@ -317,6 +318,9 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 				a_pm = (pairs ? 1u : 0u) | (R.mm << 1);
 			}
 			a_pos += R.len + 1u;
+#ifdef ANDI_WHATIF_NOCOLS
+			need_cols = false;  // timing experiment only: results are wrong
+#endif
 			op = need_cols ? OP_COLS : OP_BEGIN;
 		}
 

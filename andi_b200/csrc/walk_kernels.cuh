@@ -30,7 +30,7 @@ struct SubjectIndex {
 	TextView rs;		   // RS planes, len = N = 2n+1, mid = n
 	const u32 *SA;		   // N
 	const int32_t *LCP;	   // N + 1
-	const u32 *dir;		   // 4^K + 1
+	const u64 *dir;		   // 4^K: first SA index | count << 32 of every k-mer
 	const unsigned char *plen;  // 4^K: longest prefix of each k-mer present in RS (< K)
 	int K;				   // directory depth, 0 = none (lookups use the generic search only)
 	u32 threshold;		   // minimum anchor length for this subject
@@ -115,7 +115,8 @@ __device__ __forceinline__ MatchResult longest_match(const SubjectIndex &S, cons
 	if (!direct) return search_range<SPEC>(S, q, qpos, rem, 0, S.rs.len);
 
 	u32 key = kmer_key(cw, K);
-	u32 lo = __ldg(S.dir + key), hi = __ldg(S.dir + key + 1);
+	u64 de = __ldg(S.dir + key);
+	u32 lo = (u32)de, hi = lo + (u32)(de >> 32);
 	if (hi > lo) {
 		MatchResult r;
 		if (hi - lo <= ANDI_SCAN_MAX) {

@@ -7,12 +7,13 @@ every computing call raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libandi_b200.so"
+LIB_PATH = Path(os.environ.get("ANDI_B200_LIB", HERE / "libandi_b200.so"))  # override: kernel experiments only
 
 MODELS = {"RAW": 0, "JC": 1, "KIMURA": 2, "LOGDET": 3, "ANI": 4}
 ESA_SEARCH, ESA_FULL = 0, 1
