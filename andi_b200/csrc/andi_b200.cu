@@ -39,6 +39,15 @@ struct andi_ctx {
 	QueryView *d_queries = nullptr;
 	bool any_sep = false;
 
+	// index-build scratch, grown on demand and reused for every subject (no allocation in the
+	// steady state of andi_dist_rows)
+	struct {
+		u32 *hist = nullptr, *bstart = nullptr, *grp = nullptr, *rank = nullptr, *flags = nullptr;
+		unsigned char *amb = nullptr;
+		void *scan_tmp = nullptr;
+		size_t scan_bytes = 0, kmers_cap = 0, n_cap = 0;
+	} bs;
+
 	andi_stats st{};
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> esa_ev, walk_ev;
 	std::vector<cudaEvent_t> free_ev;
@@ -62,6 +71,8 @@ struct andi_esa {
 	Inter *cache = nullptr;
 	u32 self = 0xffffffffu;
 	u32 threshold = 0;
+	// capacities of the arrays above (an andi_esa can be rebuilt in place for another subject)
+	size_t cap_words = 0, cap_n = 0, cap_kmers = 0, cap_present = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -175,6 +186,9 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	harvest_events(ctx);
 	pool_release(ctx);
+	dfree(ctx, ctx->bs.hist), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
+	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb);
+	if (ctx->bs.scan_tmp) cudaFreeAsync(ctx->bs.scan_tmp, ctx->stream);
 	cudaStreamSynchronize(ctx->stream);
 	for (auto e : ctx->free_ev) cudaEventDestroy(e);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -364,8 +378,9 @@ extern "C" int andi_esa_build(andi_ctx *ctx, size_t subject, unsigned flags, and
 	E->has_sep = ctx->has_sep[subject] != 0;
 	E->self = (u32)subject;
 	size_t nw = plane_words(E->N);
-	if (dalloc(ctx, &E->code, nw) != cudaSuccess || dalloc(ctx, &E->spec, nw) != cudaSuccess) {
-		ctx->err = "device allocation failed";
+	E->threshold = (u32)andi_threshold(0.025, ctx->gc[subject], E->N);
+	E->K = choose_depth(E->N, E->threshold);
+	if (esa_ensure(ctx, E)) {
 		esa_release(E);
 		delete E;
 		return ANDI_ERR_NOMEM;
@@ -377,10 +392,7 @@ extern "C" int andi_esa_build(andi_ctx *ctx, size_t subject, unsigned flags, and
 	*out = E;
 	// The directory depth is tied to the default threshold (p = 0.025); a walk that is given a
 	// smaller threshold falls back to the generic search (see launch sites).
-	E->threshold = (u32)andi_threshold(0.025, ctx->gc[subject], E->N);
-	E->K = choose_depth(E->N, E->threshold);
-	int rc = ANDI_OK;
-	rc = build_index(ctx, E, flags);
+	int rc = build_index(ctx, E, flags);
 	if (rc) {
 		esa_release(E);
 		delete E;
@@ -413,6 +425,7 @@ extern "C" int andi_esa_build_rs(andi_ctx *ctx, const char *rs, size_t rs_len, u
 		delete E;
 		return ANDI_ERR_NOMEM;
 	}
+	E->cap_words = nw;
 	cudaMemcpyAsync(d_chars, rs, rs_len, cudaMemcpyHostToDevice, ctx->stream);
 	cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), ctx->stream);
 	ctx->st.h2d_bytes += rs_len;

@@ -154,7 +154,7 @@ static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
 		E->present.offset[m] = (u32)words;
 		words += (((size_t)1 << (2 * m)) + 31) / 32;
 	}
-	CK(dalloc(ctx, &E->present.bits, words));
+	(void)words;  // E->present.bits was sized by esa_ensure
 	u32 top_bits = 1u << (2 * (K - 1));
 	k_presence_from_dir<<<nblocks((top_bits + 31) / 32, 256), 256, 0, st>>>(E->dir, top_bits,
 																			 E->present.bits + E->present.offset[K - 1]);
@@ -164,9 +164,7 @@ static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
 																	   E->present.bits + E->present.offset[m]);
 	}
 	k_presence_patch<<<nblocks(E->N, 256), 256, 0, st>>>(rs, K, E->present);
-	CK(dalloc(ctx, &E->plen, kmers));
 	k_prefix_len<<<nblocks(kmers, 256), 256, 0, st>>>(E->present, K, E->plen);
-	dfree(ctx, E->present.bits);  // only the table is needed from here on
 	ctx->st.esa_launches += 3 + (K - 1);
 	return ANDI_OK;
 }
@@ -175,6 +173,7 @@ static int build_full(andi_ctx *ctx, andi_esa *E) {
 	// CLD, FVC, prefix cache: only for the reference-visible esa_s (ANDI_ESA_FULL)
 	cudaStream_t st = ctx->stream;
 	const u32 N = E->N;
+	dfree(ctx, E->CLD), dfree(ctx, E->FVC), dfree(ctx, E->cache);
 	CK(dalloc(ctx, &E->CLD, (size_t)N + 1));
 	CK(dalloc(ctx, &E->FVC, (size_t)N));
 	CK(dalloc(ctx, &E->cache, (size_t)1 << 20));
@@ -211,6 +210,65 @@ static void esa_release(andi_esa *E) {
 	dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->SA), dfree(ctx, E->LCP);
 	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->plen), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
 	dfree(ctx, E->cache);
+	E->cap_words = E->cap_n = E->cap_kmers = E->cap_present = 0;
+	E->full = false;
+}
+
+// Make sure the arrays of E can hold an index of E->N characters with directory depth E->K.
+static int esa_ensure(andi_ctx *ctx, andi_esa *E) {
+	const size_t nw = plane_words(E->N);
+	if (nw > E->cap_words) {
+		dfree(ctx, E->code), dfree(ctx, E->spec);
+		CK(dalloc(ctx, &E->code, nw));
+		CK(dalloc(ctx, &E->spec, nw));
+		E->cap_words = nw;
+	}
+	if ((size_t)E->N > E->cap_n) {
+		dfree(ctx, E->SA), dfree(ctx, E->LCP);
+		CK(dalloc(ctx, &E->SA, E->N));
+		CK(dalloc(ctx, &E->LCP, (size_t)E->N + 1));
+		E->cap_n = E->N;
+	}
+	if (E->K >= 2) {
+		const size_t kmers = (size_t)1 << (2 * E->K);
+		if (kmers > E->cap_kmers) {
+			dfree(ctx, E->dir), dfree(ctx, E->plen);
+			CK(dalloc(ctx, &E->dir, kmers));
+			CK(dalloc(ctx, &E->plen, kmers));
+			E->cap_kmers = kmers;
+		}
+		size_t words = 0;
+		for (int m = 1; m < E->K; m++) words += (((size_t)1 << (2 * m)) + 31) / 32;
+		if (words > E->cap_present) {
+			dfree(ctx, E->present.bits);
+			CK(dalloc(ctx, &E->present.bits, words));
+			E->cap_present = words;
+		}
+	}
+	return ANDI_OK;
+}
+
+static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
+	auto &b = ctx->bs;
+	if (!b.flags) CK(dalloc(ctx, &b.flags, 2));
+	if (kmers > b.kmers_cap) {
+		dfree(ctx, b.hist), dfree(ctx, b.bstart);
+		if (b.scan_tmp) cudaFreeAsync(b.scan_tmp, ctx->stream);
+		CK(dalloc(ctx, &b.hist, kmers + 1));
+		CK(dalloc(ctx, &b.bstart, kmers + 1));
+		b.scan_bytes = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, b.scan_bytes, b.hist, b.bstart, (int)(kmers + 1), ctx->stream);
+		CK(cudaMallocAsync(&b.scan_tmp, b.scan_bytes, ctx->stream));
+		b.kmers_cap = kmers;
+	}
+	if (N > b.n_cap) {
+		dfree(ctx, b.grp), dfree(ctx, b.rank), dfree(ctx, b.amb);
+		CK(dalloc(ctx, &b.grp, N));
+		CK(dalloc(ctx, &b.rank, N));
+		CK(dalloc(ctx, &b.amb, N));
+		b.n_cap = N;
+	}
+	return ANDI_OK;
 }
 
 static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
@@ -219,51 +277,40 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 	cudaStream_t st = ctx->stream;
 	const size_t kmers = (size_t)1 << (2 * K);
 	TextView rs = rs_view(E);
-	u32 *hist = nullptr, *bstart = nullptr, *cursor = nullptr, *grp = nullptr, *rank = nullptr, *flags = nullptr;
-	unsigned char *amb = nullptr;
-	CK(dalloc(ctx, &hist, kmers + 1));
-	CK(dalloc(ctx, &bstart, kmers + 1));
-	CK(dalloc(ctx, &cursor, kmers));
-	CK(dalloc(ctx, &grp, N));
-	CK(dalloc(ctx, &rank, N));
-	CK(dalloc(ctx, &amb, N));
-	CK(dalloc(ctx, &flags, 2));
-	CK(dalloc(ctx, &E->dir, kmers));
-	CK(cudaMemsetAsync(hist, 0, (kmers + 1) * sizeof(u32), st));
-	CK(cudaMemsetAsync(cursor, 0, kmers * sizeof(u32), st));
-	CK(cudaMemsetAsync(flags, 0, 2 * sizeof(u32), st));
-	size_t scan_bytes = 0;
-	cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, hist, bstart, (int)(kmers + 1), st);
-	void *tmp = nullptr;
-	CK(cudaMallocAsync(&tmp, scan_bytes, st));
-	k_bucket_hist<<<nblocks(N, 256), 256, 0, st>>>(rs, K, hist);
-	CK(cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, hist, bstart, (int)(kmers + 1), st));
-	k_bucket_scatter<<<nblocks(N, 256), 256, 0, st>>>(rs, K, bstart, cursor, E->SA);
-	k_bucket_sort<<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, bstart, E->SA, grp, rank, amb, E->dir, flags);
-	k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, flags + 1);
+	int rc = scratch_ensure(ctx, kmers, N);
+	if (rc) return rc;
+	auto &b = ctx->bs;
+	CK(cudaMemsetAsync(b.hist, 0, (kmers + 1) * sizeof(u32), st));
+	CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(u32), st));
+	k_bucket_hist<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist);
+	size_t sb = b.scan_bytes;
+	CK(cub::DeviceScan::ExclusiveSum(b.scan_tmp, sb, b.hist, b.bstart, (int)(kmers + 1), st));
+	// the histogram becomes the scatter cursor: after the scatter hist[key] = end of bucket key
+	CK(cudaMemcpyAsync(b.hist, b.bstart, kmers * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+	k_bucket_scatter<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist, E->SA);
+	k_bucket_sort<<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, b.grp, b.rank, b.amb, E->dir,
+														b.flags);
+	k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	ctx->st.esa_launches += 4;
 	ctx->st.cub_calls += 1;
-	cudaFreeAsync(tmp, st);
-	dfree(ctx, hist), dfree(ctx, cursor);
-	int rc = build_prefix_lengths(ctx, E);
+	rc = build_prefix_lengths(ctx, E);
 	u32 h_flags[2] = {0, 0};
 	if (!rc) {
-		CK(cudaMemcpyAsync(h_flags, flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_flags, b.flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 	}
 	if (!rc && h_flags[0]) {
 		// tied suffixes: refine them, then the LCP has to be taken again
-		rc = doubling_rounds(ctx, E, grp, rank, amb, (u32)K);
+		rc = doubling_rounds(ctx, E, b.grp, b.rank, b.amb, (u32)K);
 		if (!rc) {
-			CK(cudaMemsetAsync(flags + 1, 0, sizeof(u32), st));
-			k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, flags + 1);
+			CK(cudaMemsetAsync(b.flags + 1, 0, sizeof(u32), st));
+			k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 			ctx->st.esa_launches++;
-			CK(cudaMemcpyAsync(h_flags, flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(h_flags, b.flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
 		}
 	}
 	if (!rc && h_flags[1]) rc = build_lcp_phi(ctx, E);
-	dfree(ctx, bstart), dfree(ctx, grp), dfree(ctx, rank), dfree(ctx, amb), dfree(ctx, flags);
 	return rc;
 }
 
@@ -275,9 +322,8 @@ static int build_index(andi_ctx *ctx, andi_esa *E, unsigned flags) {
 		ctx->first_ev = get_event(ctx);
 		mark(ctx, ctx->first_ev);
 	}
-	CK(dalloc(ctx, &E->SA, E->N));
-	CK(dalloc(ctx, &E->LCP, (size_t)E->N + 1));
-	int rc;
+	int rc = esa_ensure(ctx, E);
+	if (rc) return rc;
 	if (E->K >= 2) {
 		rc = build_index_bucket(ctx, E);
 	} else {

@@ -41,13 +41,12 @@ __global__ void k_bucket_hist(TextView rs, int K, u32 *__restrict__ hist) {
 	atomicAdd(hist + padded_key(rs, i, K, run), 1u);
 }
 
-__global__ void k_bucket_scatter(TextView rs, int K, const u32 *__restrict__ bstart, u32 *__restrict__ cursor,
-								 u32 *__restrict__ SA) {
+__global__ void k_bucket_scatter(TextView rs, int K, u32 *__restrict__ cursor, u32 *__restrict__ SA) {
 	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= rs.len) return;
 	u32 run;
 	u32 key = padded_key(rs, i, K, run);
-	SA[bstart[key] + atomicAdd(cursor + key, 1u)] = i;
+	SA[atomicAdd(cursor + key, 1u)] = i;  // cursor starts at the bucket start
 }
 
 // Compare suffixes a != b of RS in the reference's byte order, looking at most `cap`
@@ -62,27 +61,47 @@ __device__ __forceinline__ int compare_suffixes(const TextView &rs, u32 a, u32 b
 
 // dir64[key] = first SA index of the suffixes that really start with this k-mer (no
 // separator inside) | their number << 32.
-__global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, u32 *__restrict__ SA,
+__global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
+							  u32 *__restrict__ SA,
 							  u32 *__restrict__ grp, u32 *__restrict__ rank, unsigned char *__restrict__ amb,
 							  u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous) {
 	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
 	if (key >= (1u << (2 * K))) return;
-	const u32 b = bstart[key], e = bstart[key + 1], s = e - b;
+	const u32 b = bstart[key], e = bend[key], s = e - b;
 	if (s == 0) {
 		dir64[key] = (u64)e;
 		return;
 	}
 	u32 valid = 0;
 	if (s > ANDI_SORT_MAX) {
-		// left to the doubling rounds as one group of depth K
+		// Too large for one thread: the suffixes that really start with this k-mer are left to
+		// the doubling rounds as one group of depth K. The padded ones (a separator or the text
+		// end inside their first K characters) do NOT share K characters with anything, so they
+		// are moved to the front and ordered here by direct comparison (they are few).
+		u32 front = b;
 		for (u32 j = b; j < e; j++) {
 			u32 p = SA[j], run;
 			padded_key(rs, p, K, run);
-			valid += run >= (u32)K;
-			grp[j] = b, rank[p] = b, amb[j] = 1;
+			if (run < (u32)K) {
+				SA[j] = SA[front];
+				SA[front] = p;
+				front++;
+			}
 		}
-		atomicAdd(n_ambiguous, s);
-		dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
+		valid = e - front;
+		for (u32 x = b + 1; x < front; x++) {
+			u32 cur = SA[x];
+			u32 y = x;
+			while (y > b && compare_suffixes(rs, SA[y - 1], cur, 0xffffffffu) > 0) {
+				SA[y] = SA[y - 1];
+				y--;
+			}
+			SA[y] = cur;
+		}
+		for (u32 j = b; j < front; j++) grp[j] = j, rank[SA[j]] = j, amb[j] = 0;
+		for (u32 j = front; j < e; j++) grp[j] = front, rank[SA[j]] = front, amb[j] = valid > 1;
+		if (valid > 1) atomicAdd(n_ambiguous, valid);
+		dir64[key] = (u64)front | ((u64)valid << 32);
 		return;
 	}
 	u32 v[ANDI_SORT_MAX];

@@ -164,9 +164,9 @@ static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_
 	else
 		CK(dalloc(ctx, &d_out, rows * n * 17));
 	int rc = ANDI_OK;
+	andi_esa E;	 // rebuilt in place for every subject: its arrays are allocated once
+	E.ctx = ctx;
 	for (size_t i = s_begin; i < s_end && !rc; i++) {
-		andi_esa E;
-		E.ctx = ctx;
 		E.n = (u32)ctx->len[i];
 		E.N = 2 * E.n + 1;
 		E.has_sep = ctx->has_sep[i] != 0;
@@ -174,10 +174,7 @@ static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_
 		E.threshold = (u32)andi_threshold(p_value, ctx->gc[i], E.N);
 		E.K = choose_depth(E.N, E.threshold);
 		size_t nw = plane_words(E.N);
-		if (dalloc(ctx, &E.code, nw) != cudaSuccess || dalloc(ctx, &E.spec, nw) != cudaSuccess) {
-			ctx->err = "device allocation failed";
-			rc = ANDI_ERR_NOMEM;
-		}
+		rc = esa_ensure(ctx, &E);
 		if (!rc) {
 			k_build_rs<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(ctx->pool_code + ctx->word_off[i],
 																   ctx->pool_spec + ctx->word_off[i], E.n, E.code,
@@ -190,8 +187,8 @@ static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_
 			rc = launch_walk(ctx, S, ctx->d_queries, nullptr, (u32)n, plan, E.threshold, model,
 							 ctx->any_sep || E.has_sep, d_rec, d_out + (i - s_begin) * n * 17);
 		}
-		esa_release(&E);
 	}
+	esa_release(&E);
 	if (!rc && !out_on_device) {
 		CK(cudaMemcpyAsync(out, d_out, rows * n * sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
 		ctx->st.d2h_bytes += rows * n * sizeof(andi_model);
