@@ -199,3 +199,29 @@ def test_very_large_genome_properties(ctx):
     ident, sub = got[0, 1], got[0, 2]
     assert ident[:16].sum() == n and ident[[0, 5, 10, 15]].sum() == n
     assert sub[:16].sum() == n and sub[:16].sum() - sub[[0, 5, 10, 15]].sum() == 500
+
+
+def test_pathological_repeats(ctx):
+    """Low-complexity and tandem-repeat texts: every suffix ties for thousands of characters, so
+    the bucket sorter hands everything to the doubling rounds and the direct LCP overflows into
+    the phi/Kasai path (index_host.cuh). Arrays and rows must still equal the oracle's."""
+    rng = np.random.default_rng(8)
+    poly = bytearray(b"A" * 60000 + b"C" + b"A" * 60000)
+    tandem = bytearray(b"ACGT" * 30000)
+    for k in rng.choice(len(tandem), size=25, replace=False):
+        tandem[k] = ord("G") if tandem[k] != ord("G") else ord("T")
+    mixed = bytes(synth.ACGT[synth.base_genome(40000, 5)].tobytes()) + bytes(tandem[:40000]) + b"T" * 3000
+    seqs = [bytes(poly), bytes(tandem), mixed, bytes(poly[:50000]) + b"!" + bytes(tandem[:30000])]
+    ctx.set_pool(seqs)
+    for k in (0, 1, 3):
+        o = oracle.OracleEsa(seqs[k])
+        e = ctx.esa_build(k, full=True)
+        got = e.download(full=True)
+        assert np.array_equal(got["SA"], o.array("SA")), ("SA", k)
+        assert np.array_equal(got["LCP"], o.array("LCP")), ("LCP", k)
+        assert np.array_equal(got["CLD"][:-1], o.array("CLD")[:-1]), ("CLD", k)
+        assert np.array_equal(got["FVC"], o.array("FVC")), ("FVC", k)
+        assert np.array_equal(got["cache"], o.array("cache")), ("cache", k)
+        e.free(), o.close()
+    for model in ("JC", "LOGDET"):
+        assert np.array_equal(ctx.dist_rows(model=model), oracle.rows(seqs, model)), model
