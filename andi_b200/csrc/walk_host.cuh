@@ -79,7 +79,7 @@ static int launch_walk(andi_ctx *ctx, const SubjectIndex &S, const QueryView *d_
 	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);
 	mark(ctx, ctx->last_ev);
 	ctx->st.walk_launches += 2;
-	ctx->st.pairs += nq;
+	ctx->st.pairs += (!d_query_ids && S.self < nq) ? nq - 1 : nq;  // the subject's own cell is not a walk
 	CK(cudaGetLastError());
 	return ANDI_OK;
 }

@@ -342,12 +342,19 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bytes_per_pair = 2 * ln / 4  # query + subject diagonal, 2 bits per base, read once
-    walk_ms = st["walk_ms"] / max(1, st["walk_launches"])
-    pairs_per_launch = st["pairs"] / max(1, st["walk_launches"])
+    # one "launch" = the chunk kernel plus its small reduce kernel for one subject
+    n_walks = max(1, st["walk_launches"] // 2)
+    walk_ms = st["walk_ms"] / n_walks
+    pairs_per_launch = st["pairs"] / n_walks
     achieved = pairs_per_launch * bytes_per_pair / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0
+    traffic = None
+    tf = ROOT / "profiles" / "walk_traffic.json"
+    if tf.exists() and args.workload == "c4" and not args.genomes and not args.length:
+        t_ = json.loads(tf.read_text())  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+        traffic = (t_["dram_bytes_read"] + t_["dram_bytes_write"]) * (pairs_per_launch / t_["pairs_per_launch"])
     roofline = {
-        "bound": "hbm", "kernel": "k_walk", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        "bound": "hbm", "kernel": "k_walk_chunks_fast (+ k_walk_reduce)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_pair": bytes_per_pair, "pairs_per_launch": pairs_per_launch, "launch_ms": walk_ms,
         "walk_share_of_step": st["walk_ms"] / ms if ms > 0 else None,
     }
