@@ -48,6 +48,8 @@ struct andi_ctx {
 		size_t scan_bytes = 0, kmers_cap = 0, n_cap = 0;
 	} bs;
 
+	unsigned long long *walk_counter = nullptr;  // unit dispenser of the walk kernels
+
 	andi_stats st{};
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> esa_ev, walk_ev;
 	std::vector<cudaEvent_t> free_ev;
@@ -187,7 +189,7 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	harvest_events(ctx);
 	pool_release(ctx);
 	dfree(ctx, ctx->bs.hist), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
-	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb);
+	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter);
 	if (ctx->bs.scan_tmp) cudaFreeAsync(ctx->bs.scan_tmp, ctx->stream);
 	cudaStreamSynchronize(ctx->stream);
 	for (auto e : ctx->free_ev) cudaEventDestroy(e);

@@ -126,12 +126,13 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 #endif
 __global__ void __launch_bounds__(ANDI_WALK_THREADS, ANDI_FAST_BLOCKS_PER_SM)
 k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
-				   u32 nq, u32 chunk, u32 cpq, u32 threshold, u32 *__restrict__ records) {
+				   u32 nq, u32 chunk, u32 cpq, u32 threshold, u32 *__restrict__ records,
+				   unsigned long long *__restrict__ next_unit) {
 	__shared__ u32 cells[2][16][ANDI_WALK_THREADS];
 	const u32 tid = threadIdx.x;
 	const unsigned long long total = (unsigned long long)nq * cpq;
-	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-	unsigned long long unit = (unsigned long long)blockIdx.x * blockDim.x + tid;
+	// units are handed out dynamically: their cost varies with the divergence of the pair
+	unsigned long long unit = atomicAdd(next_unit, 1ULL);
 	const u32 t = threshold, N = S.rs.len, mid = S.rs.mid, border = N / 2;
 	const int K = S.K;
 	const u64 *__restrict__ s_code = S.rs.code;
@@ -173,7 +174,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 					op = OP_BEGIN;
 					break;
 				}
-				unit += stride;
+				unit = atomicAdd(next_unit, 1ULL);
 			}
 		}
 		if (__all_sync(0xffffffffu, op == OP_IDLE)) break;
@@ -220,7 +221,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 #pragma unroll
 				for (int x = 0; x < 16; x++) rec[16 + x] = flag ? cells[1][x][tid] : 0u;
 				rec[37] = flag;
-				unit += stride;
+				unit = atomicAdd(next_unit, 1ULL);
 				op = OP_FETCH;
 			} else {
 				// process.c:86-99: the diagonal of the previous anchor, if close enough

@@ -7,7 +7,8 @@
 #pragma once
 #include "walk_fast.cuh"
 
-typedef void (*chunks_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, u32 *);
+typedef void (*chunks_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, u32 *,
+						  unsigned long long *);
 typedef void (*reduce_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, const u32 *, u32 *);
 
 static void pick_walk(int model, bool spec, chunks_fn &cf, reduce_fn &rf) {
@@ -70,8 +71,10 @@ static int launch_walk(andi_ctx *ctx, const SubjectIndex &S, const QueryView *d_
 		ctx->first_ev = get_event(ctx);
 		mark(ctx, ctx->first_ev);
 	}
+	if (!ctx->walk_counter) CK(dalloc(ctx, &ctx->walk_counter, 1));
+	CK(cudaMemsetAsync(ctx->walk_counter, 0, sizeof(unsigned long long), ctx->stream));
 	cf<<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
-													 d_records);
+													 d_records, ctx->walk_counter);
 	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
 												   d_records, d_out);
 	mark(ctx, e1);

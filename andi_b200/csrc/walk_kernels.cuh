@@ -285,12 +285,13 @@ __device__ __forceinline__ void walk_tail(const TextView &q, u32 t, const WalkSt
 template <bool QUARTER, bool SPEC>
 __global__ void __launch_bounds__(ANDI_WALK_THREADS)
 k_walk_chunks(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
-			  u32 nq, u32 chunk, u32 cpq, u32 threshold, u32 *__restrict__ records) {
+			  u32 nq, u32 chunk, u32 cpq, u32 threshold, u32 *__restrict__ records,
+				   unsigned long long *__restrict__ next_unit) {
 	__shared__ u32 cells[2][16][ANDI_WALK_THREADS];
 	const u32 tid = threadIdx.x;
 	const unsigned long long total = (unsigned long long)nq * cpq;
-	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-	unsigned long long unit = (unsigned long long)blockIdx.x * blockDim.x + tid;
+	// units are handed out dynamically: their cost varies with the divergence of the pair
+	unsigned long long unit = atomicAdd(next_unit, 1ULL);
 	const u32 t = threshold;
 
 	bool active = false;
@@ -319,7 +320,7 @@ k_walk_chunks(const SubjectIndex S, const QueryView *__restrict__ queries, const
 					for (int x = 0; x < 16; x++) cells[0][x][tid] = 0, cells[1][x][tid] = 0;
 					break;
 				}
-				unit += stride;
+				unit = atomicAdd(next_unit, 1ULL);
 			}
 		}
 		if (!__any_sync(0xffffffffu, active)) break;
@@ -368,7 +369,7 @@ k_walk_chunks(const SubjectIndex S, const QueryView *__restrict__ queries, const
 				rec[32] = E.pos_q, rec[33] = E.last_s, rec[34] = E.last_q, rec[35] = E.last_len, rec[36] = E.paired;
 				rec[37] = flag;
 				active = false;
-				unit += stride;
+				unit = atomicAdd(next_unit, 1ULL);
 			}
 		}
 		__syncwarp();
