@@ -40,6 +40,8 @@ WORKLOADS = {
     "c4": (3085, 2_100_000, 0.005, 0.02, 3085, "JC"),
     "c2": (29, 5_000_000, 0.01, 0.05, 29, "JC"),
     "c1": (2, 100_000, 0.0099, 0.0099, 1729, "JC"),
+    "c3": (109, 5_000_000, 0.01, 0.05, 109, "KIMURA"),
+    "c5": (16, 120_000_000, 0.01, 0.05, 16, "JC"),
 }
 
 
