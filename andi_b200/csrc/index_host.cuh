@@ -271,6 +271,9 @@ static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
 	return ANDI_OK;
 }
 
+// Texts above this many characters bucket through the library radix sort (tables beyond L2).
+#define ANDI_BUCKET_ATOMIC_MAX (8u << 20)
+
 static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 	const u32 N = E->N;
 	const int K = E->K;
@@ -280,19 +283,41 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 	int rc = scratch_ensure(ctx, kmers, N);
 	if (rc) return rc;
 	auto &b = ctx->bs;
-	CK(cudaMemsetAsync(b.hist, 0, (kmers + 1) * sizeof(u32), st));
 	CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(u32), st));
-	k_bucket_hist<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist);
-	size_t sb = b.scan_bytes;
-	CK(cub::DeviceScan::ExclusiveSum(b.scan_tmp, sb, b.hist, b.bstart, (int)(kmers + 1), st));
-	// the histogram becomes the scatter cursor: after the scatter hist[key] = end of bucket key
-	CK(cudaMemcpyAsync(b.hist, b.bstart, kmers * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-	k_bucket_scatter<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist, E->SA);
-	k_bucket_sort<<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, b.grp, b.rank, b.amb, E->dir,
-														b.flags);
+	if (N <= ANDI_BUCKET_ATOMIC_MAX) {
+		// counting sort with L2-resident tables: histogram, scan, scatter
+		CK(cudaMemsetAsync(b.hist, 0, (kmers + 1) * sizeof(u32), st));
+		k_bucket_hist<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist);
+		size_t sb = b.scan_bytes;
+		CK(cub::DeviceScan::ExclusiveSum(b.scan_tmp, sb, b.hist, b.bstart, (int)(kmers + 1), st));
+		// the histogram becomes the scatter cursor: after the scatter hist[key] = end of bucket key
+		CK(cudaMemcpyAsync(b.hist, b.bstart, kmers * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+		k_bucket_scatter<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist, E->SA);
+		ctx->st.esa_launches += 2;
+		ctx->st.cub_calls += 1;
+	} else {
+		// (key, position) pairs through the library radix sort, bounds from the sorted keys
+		u32 *keys_a = nullptr, *keys_b = nullptr, *idx = nullptr;
+		CK(dalloc(ctx, &keys_a, N));
+		CK(dalloc(ctx, &keys_b, N));
+		CK(dalloc(ctx, &idx, N));
+		size_t sort_bytes = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_a, keys_b, idx, E->SA, (int)N, 0, 2 * K, st);
+		void *tmp = nullptr;
+		CK(cudaMallocAsync(&tmp, sort_bytes, st));
+		k_bucket_keys<<<nblocks(N, 256), 256, 0, st>>>(rs, K, keys_a, idx);
+		CK(cub::DeviceRadixSort::SortPairs(tmp, sort_bytes, keys_a, keys_b, idx, E->SA, (int)N, 0, 2 * K, st));
+		CK(cudaMemsetAsync(b.bstart, 0, kmers * sizeof(u32), st));
+		CK(cudaMemsetAsync(b.hist, 0, kmers * sizeof(u32), st));
+		k_bucket_bounds<<<nblocks(N, 256), 256, 0, st>>>(keys_b, N, b.bstart, b.hist);
+		cudaFreeAsync(tmp, st);
+		dfree(ctx, keys_a), dfree(ctx, keys_b), dfree(ctx, idx);
+		ctx->st.esa_launches += 2;
+		ctx->st.cub_calls += 1;
+	}
+	k_bucket_sort<<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, E->dir, b.flags);
 	k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
-	ctx->st.esa_launches += 4;
-	ctx->st.cub_calls += 1;
+	ctx->st.esa_launches += 2;
 	rc = build_prefix_lengths(ctx, E);
 	u32 h_flags[2] = {0, 0};
 	if (!rc) {
@@ -300,7 +325,9 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 		CK(cudaStreamSynchronize(st));
 	}
 	if (!rc && h_flags[0]) {
-		// tied suffixes: refine them, then the LCP has to be taken again
+		// tied suffixes: materialise their groups, refine them, then take the LCP again
+		k_bucket_groups<<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, b.grp, b.rank, b.amb);
+		ctx->st.esa_launches++;
 		rc = doubling_rounds(ctx, E, b.grp, b.rank, b.amb, (u32)K);
 		if (!rc) {
 			CK(cudaMemsetAsync(b.flags + 1, 0, sizeof(u32), st));

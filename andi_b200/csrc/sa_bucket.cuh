@@ -59,17 +59,36 @@ __device__ __forceinline__ int compare_suffixes(const TextView &rs, u32 a, u32 b
 	return sa < sb ? -1 : 1;  // different suffixes always differ here (end of text ranks lowest)
 }
 
+// Large texts: the histogram / cursor tables no longer fit in L2 and the atomics above turn into
+// random DRAM traffic. There the bucketing pass is a library radix sort of (key, position)
+// pairs (cub::DeviceRadixSort, 2K key bits) and the bucket bounds are read off the sorted keys
+// -- sequential writes, because the keys ascend.
+__global__ void k_bucket_keys(TextView rs, int K, u32 *__restrict__ keys, u32 *__restrict__ idx) {
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= rs.len) return;
+	u32 run;
+	keys[i] = padded_key(rs, i, K, run);
+	idx[i] = i;
+}
+
+__global__ void k_bucket_bounds(const u32 *__restrict__ keys, u32 N, u32 *__restrict__ bstart, u32 *__restrict__ bend) {
+	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= N) return;
+	u32 k = keys[j];
+	if (j == 0 || keys[j - 1] != k) bstart[k] = j;
+	if (j + 1 == N || keys[j + 1] != k) bend[k] = j + 1;
+}
+
 // dir64[key] = first SA index of the suffixes that really start with this k-mer (no
-// separator inside) | their number << 32.
+// separator inside) | their number << 32. *n_ambiguous counts the suffixes that are still tied
+// with a neighbour; their groups are materialised by k_bucket_groups only when there are any.
 __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
-							  u32 *__restrict__ SA,
-							  u32 *__restrict__ grp, u32 *__restrict__ rank, unsigned char *__restrict__ amb,
-							  u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous) {
+							  u32 *__restrict__ SA, u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous) {
 	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
 	if (key >= (1u << (2 * K))) return;
 	const u32 b = bstart[key], e = bend[key], s = e - b;
 	if (s == 0) {
-		dir64[key] = (u64)e;
+		dir64[key] = 0;
 		return;
 	}
 	u32 valid = 0;
@@ -98,8 +117,6 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 			}
 			SA[y] = cur;
 		}
-		for (u32 j = b; j < front; j++) grp[j] = j, rank[SA[j]] = j, amb[j] = 0;
-		for (u32 j = front; j < e; j++) grp[j] = front, rank[SA[j]] = front, amb[j] = valid > 1;
 		if (valid > 1) atomicAdd(n_ambiguous, valid);
 		dir64[key] = (u64)front | ((u64)valid << 32);
 		return;
@@ -117,26 +134,50 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 		}
 		v[y] = cur;
 	}
-	// tie bit x: v[x] agrees with v[x-1] on the first ANDI_SORT_CAP characters
-	u32 ties = 0;
-	for (u32 x = 1; x < s; x++)
-		if (compare_suffixes(rs, v[x - 1], v[x], ANDI_SORT_CAP) == 0) ties |= 1u << x;
-	u32 head = b, tied = 0;
+	u32 tied = 0;
 	for (u32 x = 0; x < s; x++) {
 		u32 p = v[x], run;
 		padded_key(rs, p, K, run);
 		valid += run >= (u32)K;
+		if (s > 1) SA[b + x] = p;
+		if (x > 0 && compare_suffixes(rs, v[x - 1], p, ANDI_SORT_CAP) == 0) tied++;
+	}
+	if (tied) atomicAdd(n_ambiguous, tied + 1);
+	dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
+}
+
+// Only when k_bucket_sort reported ties: group heads, ranks and "ambiguous" flags of every
+// suffix, the input of the doubling rounds (index_host.cuh). Buckets are laid out as
+// k_bucket_sort left them.
+__global__ void k_bucket_groups(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
+								const u32 *__restrict__ SA, u32 *__restrict__ grp, u32 *__restrict__ rank,
+								unsigned char *__restrict__ amb) {
+	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
+	if (key >= (1u << (2 * K))) return;
+	const u32 b = bstart[key], e = bend[key], s = e - b;
+	if (s == 0) return;
+	if (s > ANDI_SORT_MAX) {
+		u32 front = b;
+		for (; front < e; front++) {
+			u32 run;
+			padded_key(rs, SA[front], K, run);
+			if (run >= (u32)K) break;
+		}
+		for (u32 j = b; j < front; j++) grp[j] = j, rank[SA[j]] = j, amb[j] = 0;
+		for (u32 j = front; j < e; j++) grp[j] = front, rank[SA[j]] = front, amb[j] = (e - front) > 1;
+		return;
+	}
+	u32 ties = 0;  // bit x: SA[b+x] agrees with SA[b+x-1] on the first ANDI_SORT_CAP characters
+	for (u32 x = 1; x < s; x++)
+		if (compare_suffixes(rs, SA[b + x - 1], SA[b + x], ANDI_SORT_CAP) == 0) ties |= 1u << x;
+	u32 head = b;
+	for (u32 x = 0; x < s; x++) {
 		bool same = (ties >> x) & 1u;
 		if (!same) head = b + x;
-		SA[b + x] = p;
 		grp[b + x] = head;
-		rank[p] = head;
-		bool a = same || ((ties >> (x + 1)) & 1u);
-		amb[b + x] = a;
-		tied += a;
+		rank[SA[b + x]] = head;
+		amb[b + x] = same || ((ties >> (x + 1)) & 1u);
 	}
-	if (tied) atomicAdd(n_ambiguous, tied);
-	dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
 }
 
 // LCP[j] = lcp(SA[j-1], SA[j]) by direct comparison, at most `cap` characters; pairs that reach
