@@ -296,9 +296,6 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 				a_pm = (pairs ? 1u : 0u) | (R.mm << 1);
 			}
 			a_pos += R.len + 1u;
-#ifdef ANDI_WHATIF_NOCOLS
-			need_cols = false;  // timing experiment only: results are wrong
-#endif
 			op = need_cols ? OP_COLS : OP_BEGIN;
 		}
 
