@@ -186,18 +186,6 @@ __global__ void k_phi(const u32 *__restrict__ SA, u32 N, int32_t *__restrict__ p
 	phi[SA[j]] = j ? (int32_t)SA[j - 1] : -1;
 }
 
-// Longest possible common prefix of two different suffixes a, b of RS when the planes are
-// not consulted for '#': the shorter suffix ends, or '#' faces another character.
-__device__ __forceinline__ u32 pair_limit_fast(const TextView &rs, u32 a, u32 b) {
-	u32 lo = a < b ? a : b, hi = a < b ? b : a;
-	u32 lim = rs.len - hi;
-	if (hi <= rs.mid)
-		lim = min(lim, rs.mid - hi);
-	else if (lo <= rs.mid)
-		lim = min(lim, rs.mid - lo);
-	return lim;
-}
-
 template <bool SPEC>
 __global__ void k_plcp(TextView rs, int32_t *__restrict__ phi_plcp) {
 	u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,8 +254,12 @@ struct PresenceLevels {
 	u32 offset[16];	 // word offset of level m
 };
 
-__global__ void k_presence_patch(TextView rs, int K, PresenceLevels lv) {
+// Positions [first, first + count) are examined (all of the text when separators may be anywhere,
+// just the K positions in front of '#' and of the text end otherwise).
+__global__ void k_presence_patch(TextView rs, int K, PresenceLevels lv, u32 first, u32 count) {
 	u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= count) return;
+	p += first;
 	if (p >= rs.len) return;
 	// run = number of nucleotides starting at p before a separator / the end (capped at K)
 	u64 sw = window32(rs.spec, p);

@@ -163,7 +163,14 @@ static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
 		k_presence_down<<<nblocks((nb + 31) / 32, 256), 256, 0, st>>>(E->present.bits + E->present.offset[m + 1], nb,
 																	   E->present.bits + E->present.offset[m]);
 	}
-	k_presence_patch<<<nblocks(E->N, 256), 256, 0, st>>>(rs, K, E->present);
+	if (E->has_sep) {
+		k_presence_patch<<<nblocks(E->N, 256), 256, 0, st>>>(rs, K, E->present, 0, E->N);
+	} else {
+		// only the K positions in front of '#' and of the text end can hold a shorter run
+		u32 k = (u32)K;
+		k_presence_patch<<<1, 32, 0, st>>>(rs, K, E->present, E->n >= k ? E->n - k : 0, k + 1);
+		k_presence_patch<<<1, 32, 0, st>>>(rs, K, E->present, E->N >= k ? E->N - k : 0, k + 1);
+	}
 	k_prefix_len<<<nblocks(kmers, 256), 256, 0, st>>>(E->present, K, E->plen);
 	ctx->st.esa_launches += 3 + (K - 1);
 	return ANDI_OK;
@@ -315,8 +322,13 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 		ctx->st.esa_launches += 2;
 		ctx->st.cub_calls += 1;
 	}
-	k_bucket_sort<<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, E->dir, b.flags);
-	k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
+	if (E->has_sep) {
+		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, E->dir, b.flags);
+		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
+	} else {
+		k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, E->dir, b.flags);
+		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
+	}
 	ctx->st.esa_launches += 2;
 	rc = build_prefix_lengths(ctx, E);
 	u32 h_flags[2] = {0, 0};
@@ -326,12 +338,18 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 	}
 	if (!rc && h_flags[0]) {
 		// tied suffixes: materialise their groups, refine them, then take the LCP again
-		k_bucket_groups<<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, b.grp, b.rank, b.amb);
+		if (E->has_sep)
+			k_bucket_groups<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, b.grp, b.rank, b.amb);
+		else
+			k_bucket_groups<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, b.grp, b.rank, b.amb);
 		ctx->st.esa_launches++;
 		rc = doubling_rounds(ctx, E, b.grp, b.rank, b.amb, (u32)K);
 		if (!rc) {
 			CK(cudaMemsetAsync(b.flags + 1, 0, sizeof(u32), st));
-			k_lcp_direct<<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
+			if (E->has_sep)
+				k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
+			else
+				k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 			ctx->st.esa_launches++;
 			CK(cudaMemcpyAsync(h_flags, b.flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));

@@ -51,12 +51,25 @@ __global__ void k_bucket_scatter(TextView rs, int K, u32 *__restrict__ cursor, u
 
 // Compare suffixes a != b of RS in the reference's byte order, looking at most `cap`
 // characters deep. Returns <0, >0, or 0 when they agree on the first `cap` characters.
+// SPEC=false: RS holds no separator but '#' (handled by position, no spec-plane loads).
+template <bool SPEC>
 __device__ __forceinline__ int compare_suffixes(const TextView &rs, u32 a, u32 b, u32 cap) {
-	u32 lim = min(cap, rs.len - max(a, b));
-	u32 m = match_len<true>(rs, a, rs, b, lim);
+	u32 lim = min(cap, SPEC ? rs.len - max(a, b) : pair_limit_fast(rs, a, b));
+	u32 m = match_len<SPEC>(rs, a, rs, b, lim);
 	if (m == cap) return 0;
-	u32 sa = sym3<true>(rs, a + m), sb = sym3<true>(rs, b + m);
+	u32 sa = sym3<SPEC>(rs, a + m), sb = sym3<SPEC>(rs, b + m);
 	return sa < sb ? -1 : 1;  // different suffixes always differ here (end of text ranks lowest)
+}
+
+// Does the suffix at p have a separator or the text end inside its first K characters?
+template <bool SPEC>
+__device__ __forceinline__ bool is_padded(const TextView &rs, u32 p, int K) {
+	if (SPEC) {
+		u32 run;
+		padded_key(rs, p, K, run);
+		return run < (u32)K;
+	}
+	return p + (u32)K > rs.len || (p <= rs.mid && rs.mid < p + (u32)K);
 }
 
 // Large texts: the histogram / cursor tables no longer fit in L2 and the atomics above turn into
@@ -82,6 +95,7 @@ __global__ void k_bucket_bounds(const u32 *__restrict__ keys, u32 N, u32 *__rest
 // dir64[key] = first SA index of the suffixes that really start with this k-mer (no
 // separator inside) | their number << 32. *n_ambiguous counts the suffixes that are still tied
 // with a neighbour; their groups are materialised by k_bucket_groups only when there are any.
+template <bool SPEC>
 __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
 							  u32 *__restrict__ SA, u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous) {
 	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,9 +113,8 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 		// are moved to the front and ordered here by direct comparison (they are few).
 		u32 front = b;
 		for (u32 j = b; j < e; j++) {
-			u32 p = SA[j], run;
-			padded_key(rs, p, K, run);
-			if (run < (u32)K) {
+			u32 p = SA[j];
+			if (is_padded<SPEC>(rs, p, K)) {
 				SA[j] = SA[front];
 				SA[front] = p;
 				front++;
@@ -111,7 +124,7 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 		for (u32 x = b + 1; x < front; x++) {
 			u32 cur = SA[x];
 			u32 y = x;
-			while (y > b && compare_suffixes(rs, SA[y - 1], cur, 0xffffffffu) > 0) {
+			while (y > b && compare_suffixes<SPEC>(rs, SA[y - 1], cur, 0xffffffffu) > 0) {
 				SA[y] = SA[y - 1];
 				y--;
 			}
@@ -128,7 +141,7 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 	for (u32 x = 1; x < s; x++) {
 		u32 cur = v[x];
 		u32 y = x;
-		while (y > 0 && compare_suffixes(rs, v[y - 1], cur, ANDI_SORT_CAP) > 0) {
+		while (y > 0 && compare_suffixes<SPEC>(rs, v[y - 1], cur, ANDI_SORT_CAP) > 0) {
 			v[y] = v[y - 1];
 			y--;
 		}
@@ -136,11 +149,10 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 	}
 	u32 tied = 0;
 	for (u32 x = 0; x < s; x++) {
-		u32 p = v[x], run;
-		padded_key(rs, p, K, run);
-		valid += run >= (u32)K;
+		u32 p = v[x];
+		valid += !is_padded<SPEC>(rs, p, K);
 		if (s > 1) SA[b + x] = p;
-		if (x > 0 && compare_suffixes(rs, v[x - 1], p, ANDI_SORT_CAP) == 0) tied++;
+		if (x > 0 && compare_suffixes<SPEC>(rs, v[x - 1], p, ANDI_SORT_CAP) == 0) tied++;
 	}
 	if (tied) atomicAdd(n_ambiguous, tied + 1);
 	dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
@@ -149,6 +161,7 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 // Only when k_bucket_sort reported ties: group heads, ranks and "ambiguous" flags of every
 // suffix, the input of the doubling rounds (index_host.cuh). Buckets are laid out as
 // k_bucket_sort left them.
+template <bool SPEC>
 __global__ void k_bucket_groups(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
 								const u32 *__restrict__ SA, u32 *__restrict__ grp, u32 *__restrict__ rank,
 								unsigned char *__restrict__ amb) {
@@ -159,9 +172,7 @@ __global__ void k_bucket_groups(TextView rs, int K, const u32 *__restrict__ bsta
 	if (s > ANDI_SORT_MAX) {
 		u32 front = b;
 		for (; front < e; front++) {
-			u32 run;
-			padded_key(rs, SA[front], K, run);
-			if (run >= (u32)K) break;
+			if (!is_padded<SPEC>(rs, SA[front], K)) break;
 		}
 		for (u32 j = b; j < front; j++) grp[j] = j, rank[SA[j]] = j, amb[j] = 0;
 		for (u32 j = front; j < e; j++) grp[j] = front, rank[SA[j]] = front, amb[j] = (e - front) > 1;
@@ -169,7 +180,7 @@ __global__ void k_bucket_groups(TextView rs, int K, const u32 *__restrict__ bsta
 	}
 	u32 ties = 0;  // bit x: SA[b+x] agrees with SA[b+x-1] on the first ANDI_SORT_CAP characters
 	for (u32 x = 1; x < s; x++)
-		if (compare_suffixes(rs, SA[b + x - 1], SA[b + x], ANDI_SORT_CAP) == 0) ties |= 1u << x;
+		if (compare_suffixes<SPEC>(rs, SA[b + x - 1], SA[b + x], ANDI_SORT_CAP) == 0) ties |= 1u << x;
 	u32 head = b;
 	for (u32 x = 0; x < s; x++) {
 		bool same = (ties >> x) & 1u;
@@ -183,6 +194,7 @@ __global__ void k_bucket_groups(TextView rs, int K, const u32 *__restrict__ bsta
 // LCP[j] = lcp(SA[j-1], SA[j]) by direct comparison, at most `cap` characters; pairs that reach
 // the cap raise *overflow and the caller recomputes everything through the phi array
 // (src/esa.c:373-426, k_phi / k_plcp) -- only repeat-rich texts get there.
+template <bool SPEC>
 __global__ void k_lcp_direct(TextView rs, const u32 *__restrict__ SA, u32 cap, int32_t *__restrict__ LCP,
 							 u32 *__restrict__ overflow) {
 	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,8 +204,8 @@ __global__ void k_lcp_direct(TextView rs, const u32 *__restrict__ SA, u32 cap, i
 		return;
 	}
 	u32 a = SA[j - 1], b = SA[j];
-	u32 lim = min(cap, rs.len - max(a, b));
-	u32 m = match_len<true>(rs, a, rs, b, lim);
+	u32 lim = min(cap, SPEC ? rs.len - max(a, b) : pair_limit_fast(rs, a, b));
+	u32 m = match_len<SPEC>(rs, a, rs, b, lim);
 	if (m == cap) atomicExch(overflow, 1u);
 	LCP[j] = (int32_t)m;
 }

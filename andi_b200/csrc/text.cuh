@@ -82,6 +82,18 @@ __device__ __forceinline__ u32 rs_run(const TextView &rs, u32 p) {
 	return rs.len - p;
 }
 
+// Longest possible common prefix of two different suffixes a, b of RS when the planes are
+// not consulted for '#': the shorter suffix ends, or '#' faces another character.
+__device__ __forceinline__ u32 pair_limit_fast(const TextView &rs, u32 a, u32 b) {
+	u32 lo = a < b ? a : b, hi = a < b ? b : a;
+	u32 lim = rs.len - hi;
+	if (hi <= rs.mid)
+		lim = min(lim, rs.mid - hi);
+	else if (lo <= rs.mid)
+		lim = min(lim, rs.mid - lo);
+	return lim;
+}
+
 // First k characters (k <= 16) of a window as an integer with the FIRST character most
 // significant, i.e. monotone in lexicographic order. Used as k-mer directory key.
 __device__ __forceinline__ u32 kmer_key(u64 win, int k) {
