@@ -225,3 +225,36 @@ def test_pathological_repeats(ctx):
         e.free(), o.close()
     for model in ("JC", "LOGDET"):
         assert np.array_equal(ctx.dist_rows(model=model), oracle.rows(seqs, model)), model
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_randomised_pools(ctx, seed, monkeypatch):
+    """Many small random inputs in one pool: random lengths (30 .. 6000), divergences, indels,
+    contig separators, reverse complements, duplicates -- all ordered pairs against the oracle,
+    with a chunk length small enough that most pairs span several chunks."""
+    monkeypatch.setenv("ANDI_B200_CHUNK", "512")
+    rng = np.random.default_rng(seed)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    base = synth.ACGT[synth.base_genome(6000, 100 + seed)].tobytes()
+    seqs = []
+    for k in range(26):
+        ln = int(rng.integers(30, 6000))
+        start = int(rng.integers(0, 6000 - ln + 1))
+        codes = np.array([b"ACGT".index(c) for c in base[start : start + ln]], np.uint8)
+        s = synth.ACGT[synth.mutate(codes, float(rng.uniform(0, 0.08)), seed * 1000 + k)].tobytes()
+        r = rng.random()
+        if r < 0.25:
+            s = synth.with_indels(s, int(rng.integers(1, 6)), 20, seed * 77 + k)
+        elif r < 0.45 and len(s) > 200:
+            s = synth.join_contigs(s, int(rng.integers(2, 6)), seed * 55 + k)
+        elif r < 0.6:
+            s = s.translate(comp)[::-1]
+        elif r < 0.65 and seqs:
+            s = seqs[int(rng.integers(0, len(seqs)))]
+        seqs.append(s)
+    for model in ("JC", "LOGDET"):
+        ctx.set_pool(seqs)
+        got = ctx.dist_rows(model=model)
+        want = oracle.rows(seqs, model)
+        bad = np.argwhere((got != want).any(axis=2))
+        assert len(bad) == 0, (model, bad[:5].tolist(), [len(seqs[i]) for i in bad[0]])
