@@ -26,13 +26,18 @@ struct TextView {
 	u32 mid;  // RS only: index of '#' (== forward length n); 0xffffffff for plain sequences
 };
 
-// 32 characters starting at pos (character 0 in the low bits).
+// 32 characters starting at pos (character 0 in the low bits): bits [2*(pos&31), +64) of the
+// 128-bit pair (w[i+1] : w[i]), taken with two 32-bit funnel shifts. The second word is always
+// loaded (the guard words make that safe); that is cheaper than branching on an aligned pos.
 __device__ __forceinline__ u64 window32(const u64 *__restrict__ w, u32 pos) {
 	u32 i = pos >> 5, sh = (pos & 31u) * 2u;
-	u64 a = __ldg(w + i);
-	if (sh == 0) return a;
-	u64 b = __ldg(w + i + 1);
-	return (a >> sh) | (b << (64u - sh));
+	u64 a = __ldg(w + i), b = __ldg(w + i + 1);
+	u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+	bool upper = sh >= 32u;
+	u32 x0 = upper ? a1 : a0, x1 = upper ? b0 : a1, x2 = upper ? b1 : b0;
+	u32 s = sh & 31u;
+	u32 lo = __funnelshift_r(x0, x1, s), hi = __funnelshift_r(x1, x2, s);
+	return ((u64)hi << 32) | lo;
 }
 
 __device__ __forceinline__ u32 code_at(const u64 *__restrict__ w, u32 pos) {
@@ -49,8 +54,7 @@ __device__ __forceinline__ u32 match_len(const TextView &a, u32 pa, const TextVi
 	while (k < limit) {
 		u64 x = window32(a.code, pa + k) ^ window32(b.code, pb + k);
 		if (SPEC) x |= window32(a.spec, pa + k) ^ window32(b.spec, pb + k);
-		x = (x | (x >> 1)) & ANDI_EVEN_BITS;
-		if (x) {
+		if (x) {  // lowest set bit sits in the 2-bit pair of the first differing character
 			k += (u32)(__ffsll((long long)x) - 1) >> 1;
 			return k < limit ? k : limit;
 		}

@@ -58,19 +58,19 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 	u64 qw = window32(q_code, a_pos + C.ck);
 	u64 sw = window32(s_code, C.cs + C.ck);
 	if (C.ck == 0 && !C.is_cand) L.key = K > 0 ? kmer_key(qw, K) : 0u;
-	u32 left = C.clim - C.ck;
+	// first differing base of the window (a differing 2-bit code has its lowest set bit at 2d or 2d+1)
 	u64 x = qw ^ sw;
-	x = (x | (x >> 1)) & ANDI_EVEN_BITS;
-	if (left < 32u) x |= 1ULL << (2u * left);
+	u32 left = C.clim - C.ck;
+	u32 d = x ? (u32)(__ffsll((long long)x) - 1) >> 1 : 32u;
 	u32 len, mm = 0;
-	if (x) {
-		u32 d = (u32)(__ffsll((long long)x) - 1) >> 1;
+	if (d >= left) {
+		len = C.clim;  // the limit (end of query / '#' / end of RS) ends the match
+	} else if (d < 32u) {
 		len = C.ck + d;
-		if (d < left) mm = ANDI_MM_VALID | ((((u32)(sw >> (2u * d))) & 3u) << 2) | (((u32)(qw >> (2u * d))) & 3u);
+		mm = ANDI_MM_VALID | ((((u32)(sw >> (2u * d))) & 3u) << 2) | (((u32)(qw >> (2u * d))) & 3u);
 	} else {
 		C.ck += 32u;
-		if (C.ck != C.clim) return;	 // compare continues
-		len = C.clim;
+		return;	 // compare continues
 	}
 	if (!C.is_cand) {
 		if (len >= t) {
