@@ -6,6 +6,7 @@
 // are CUB device primitives (library code, like cuBLAS for a GEMM); every other kernel is ours.
 #include "../../include/andi_b200.h"
 #include "walk_kernels.cuh"
+#include "pack_tma.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -258,12 +259,33 @@ static int pool_finish(andi_ctx *ctx, const unsigned char *d_chars, const std::v
 	unsigned long long *d_cnt = nullptr;
 	CK(dalloc(ctx, &d_cnt, 2 * n));
 	CK(cudaMemsetAsync(d_cnt, 0, 2 * n * sizeof(unsigned long long), ctx->stream));
-	for (size_t k = 0; k < n; k++) {
-		u32 nw = (u32)plane_words(ctx->len[k]);
-		k_pack<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(d_chars + offs[k], (u32)ctx->len[k],
-														   ctx->pool_code + ctx->word_off[k],
-														   ctx->pool_spec + ctx->word_off[k], nw, d_cnt + 2 * k);
+	// one TMA-staged launch for all full 8 KiB tiles of 16-byte aligned sequences, one launch for
+	// the tails (pack_tma.cuh)
+	{
+		std::vector<PackSeq> ps(n);
+		std::vector<u32> full(n);
+		u32 ntiles = 0;
+		for (size_t k = 0; k < n; k++) {
+			bool aligned = ((uintptr_t)(d_chars + offs[k]) & 15u) == 0;
+			full[k] = aligned ? (u32)(ctx->len[k] / ANDI_PACK_TILE) : 0u;
+			ps[k].char_off = offs[k], ps[k].word_off = ctx->word_off[k], ps[k].len = (u32)ctx->len[k], ps[k].tile0 = ntiles;
+			ntiles += full[k];
+		}
+		PackSeq *d_ps = nullptr;
+		u32 *d_full = nullptr;
+		CK(dalloc(ctx, &d_ps, n));
+		CK(dalloc(ctx, &d_full, n));
+		CK(cudaMemcpyAsync(d_ps, ps.data(), n * sizeof(PackSeq), cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(d_full, full.data(), n * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+		if (ntiles) {
+			unsigned grid = std::min<unsigned>(ntiles, (unsigned)ctx->sm_count * 4u);
+			k_pack_tma<<<grid, 256, 0, ctx->stream>>>(d_chars, d_ps, (u32)n, ntiles, ctx->pool_code, ctx->pool_spec, d_cnt);
+			ctx->st.esa_launches++;
+		}
+		k_pack_tails<<<(unsigned)n, 256, 0, ctx->stream>>>(d_chars, d_ps, d_full, ctx->pool_code, ctx->pool_spec, d_cnt);
 		ctx->st.esa_launches++;
+		CK(cudaStreamSynchronize(ctx->stream));	 // ps / full go out of scope
+		dfree(ctx, d_ps), dfree(ctx, d_full);
 	}
 	std::vector<unsigned long long> cnt(2 * n);
 	CK(cudaMemcpyAsync(cnt.data(), d_cnt, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
