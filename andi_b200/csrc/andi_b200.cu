@@ -37,6 +37,8 @@ struct andi_ctx {
 	std::vector<int> has_sep;
 	std::vector<size_t> word_off;  // u64-word offset of each sequence's planes
 	u64 *pool_code = nullptr, *pool_spec = nullptr;
+	size_t pool_words = 0;
+	uint4 *pool_comp = nullptr;	 // prefix composition per word, built on first LOGDET / ANI use
 	QueryView *d_queries = nullptr;
 	bool any_sep = false;
 
@@ -177,6 +179,7 @@ extern "C" int andi_ctx_create(int device, void *stream, andi_ctx **out) {
 static void pool_release(andi_ctx *ctx) {
 	dfree(ctx, ctx->pool_code);
 	dfree(ctx, ctx->pool_spec);
+	dfree(ctx, ctx->pool_comp);
 	dfree(ctx, ctx->d_queries);
 	ctx->n = 0;
 	ctx->len.clear(), ctx->gc.clear(), ctx->has_sep.clear(), ctx->word_off.clear();
@@ -256,6 +259,7 @@ static int pool_finish(andi_ctx *ctx, const unsigned char *d_chars, const std::v
 	}
 	CK(dalloc(ctx, &ctx->pool_code, words));
 	CK(dalloc(ctx, &ctx->pool_spec, words));
+	ctx->pool_words = words;
 	unsigned long long *d_cnt = nullptr;
 	CK(dalloc(ctx, &d_cnt, 2 * n));
 	CK(cudaMemsetAsync(d_cnt, 0, 2 * n * sizeof(unsigned long long), ctx->stream));
@@ -519,6 +523,7 @@ static SubjectIndex subject_index(const andi_esa *E) {
 	S.rs = rs_view(E);
 	S.SA = E->SA, S.LCP = E->LCP, S.dir = E->dir, S.plen = E->plen;
 	S.K = E->K, S.threshold = E->threshold, S.self = E->self, S.has_sep = E->has_sep;
+	S.qcode_base = nullptr, S.qcomp_base = nullptr;
 	return S;
 }
 

@@ -40,6 +40,19 @@ __device__ __forceinline__ u64 window32(const u64 *__restrict__ w, u32 pos) {
 	return ((u64)hi << 32) | lo;
 }
 
+// 64 characters starting at pos (three word loads): lo = characters 0..31, hi = 32..63.
+// The caller guarantees pos < text length, so word (pos>>5)+2 is inside the guarded plane.
+__device__ __forceinline__ void window64(const u64 *__restrict__ w, u32 pos, u64 &lo, u64 &hi) {
+	u32 i = pos >> 5, sh = (pos & 31u) * 2u;
+	u64 a = __ldg(w + i), b = __ldg(w + i + 1), c = __ldg(w + i + 2);
+	u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), c0 = (u32)c, c1 = (u32)(c >> 32);
+	bool upper = sh >= 32u;
+	u32 x0 = upper ? a1 : a0, x1 = upper ? b0 : a1, x2 = upper ? b1 : b0, x3 = upper ? c0 : b1, x4 = upper ? c1 : c0;
+	u32 s = sh & 31u;
+	lo = ((u64)__funnelshift_r(x1, x2, s) << 32) | __funnelshift_r(x0, x1, s);
+	hi = ((u64)__funnelshift_r(x3, x4, s) << 32) | __funnelshift_r(x2, x3, s);
+}
+
 __device__ __forceinline__ u32 code_at(const u64 *__restrict__ w, u32 pos) {
 	return (u32)(__ldg(w + (pos >> 5)) >> ((pos & 31u) * 2u)) & 3u;
 }

@@ -1,8 +1,9 @@
 // andi_b200/csrc/walk_fast.cuh -- k_walk_chunks_fast: the chunked anchor walk of
 // walk_kernels.cuh as a phase pipeline with carry-over.
 //
-// Same units, same records, same results as k_walk_chunks<QUARTER=true, SPEC=false> (RAW / JC /
-// KIMURA counting, no '!' in subject or queries -- the headline configuration). What changes
+// Same units, same records, same results as k_walk_chunks<QUARTER, SPEC=false> (no '!' in
+// subject or queries; QUARTER = RAW / JC / KIMURA counting is the headline configuration,
+// !QUARTER = LOGDET / ANI needs the pool's prefix-composition table). What changes
 // is the execution shape. In the straightforward kernel every lane runs nested while-loops
 // (window compares of different lengths, bucket scans, bitmap probes) and the warp waits for
 // its slowest lane at every level: ncu showed 6 of 32 lanes active. A pure lane-level state
@@ -15,13 +16,13 @@
 //         -> COLS
 //
 // A lane flows through as many consecutive phases as its walk step needs -- the common steps
-// (lucky anchor within two windows; lucky miss -> directory -> one candidate) complete in ONE
+// (lucky anchor within two 64-base windows; lucky miss -> directory -> one candidate) complete in ONE
 // trip -- and only carries over into the next trip when it needs a phase again (a long
 // compare, a second candidate, more gap columns). Nobody waits for a loop, and lanes stay
 // aligned at step boundaries, so BEGIN / CMP / DECIDE run with most of the warp.
 //
 //   BEGIN   chunk/phase bookkeeping, then set up the lucky compare (process.c:86-99)
-//   CMP     one 32-base window of a compare (lucky diagonal or directory candidate)
+//   CMP     one 64-base window of a compare (lucky diagonal or directory candidate)
 //   DIR     k-mer directory + prefix-length probe      CAND   fetch SA[candidate]
 //   SLOW    anything unusual -> longest_match<false>() of walk_kernels.cuh
 //   DECIDE  process.c:160-196: pairing, accounting, advance
@@ -49,27 +50,31 @@ struct LaneResult {
 	u32 s, len, mm, found;
 };
 
-// One 32-base window of the current compare; sets `op` when the compare has ended.
+// One 64-base window of the current compare; sets `op` when the compare has ended.
 __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &L, LaneResult &R,
 										   const u64 *__restrict__ q_code, const u64 *__restrict__ s_code, u32 a_pos,
 										   u32 qlen, u32 t, int K) {
-	// plain two-word window loads: they hit L1/L2, and a register cache of the last words costs
-	// more instructions and registers than it saves (measured: +14 % throughput without it)
-	u64 qw = window32(q_code, a_pos + C.ck);
-	u64 sw = window32(s_code, C.cs + C.ck);
-	if (C.ck == 0 && !C.is_cand) L.key = K > 0 ? kmer_key(qw, K) : 0u;
+	// plain window loads (three words = 64 bases per text): they hit L1/L2, and a register cache
+	// of the last words costs more instructions and registers than it saves (measured: +14 %
+	// throughput without it). 64 bases end 96 % of all compares in one pass.
+	u64 q0, q1, s0, s1;
+	window64(q_code, a_pos + C.ck, q0, q1);
+	window64(s_code, C.cs + C.ck, s0, s1);
+	if (C.ck == 0 && !C.is_cand) L.key = K > 0 ? kmer_key(q0, K) : 0u;
 	// first differing base of the window (a differing 2-bit code has its lowest set bit at 2d or 2d+1)
-	u64 x = qw ^ sw;
+	u64 x0 = q0 ^ s0, x1 = q1 ^ s1;
 	u32 left = C.clim - C.ck;
-	u32 d = x ? (u32)(__ffsll((long long)x) - 1) >> 1 : 32u;
+	u32 d = x0 ? (u32)(__ffsll((long long)x0) - 1) >> 1 : (x1 ? 32u + ((u32)(__ffsll((long long)x1) - 1) >> 1) : 64u);
 	u32 len, mm = 0;
 	if (d >= left) {
 		len = C.clim;  // the limit (end of query / '#' / end of RS) ends the match
-	} else if (d < 32u) {
+	} else if (d < 64u) {
 		len = C.ck + d;
-		mm = ANDI_MM_VALID | ((((u32)(sw >> (2u * d))) & 3u) << 2) | (((u32)(qw >> (2u * d))) & 3u);
+		u64 sw = d < 32u ? s0 : s1, qw = d < 32u ? q0 : q1;
+		u32 sh = 2u * (d & 31u);
+		mm = ANDI_MM_VALID | ((((u32)(sw >> sh)) & 3u) << 2) | (((u32)(qw >> sh)) & 3u);
 	} else {
-		C.ck += 32u;
+		C.ck += 64u;
 		return;	 // compare continues
 	}
 	if (!C.is_cand) {
@@ -104,7 +109,8 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 #ifndef ANDI_FAST_BLOCKS_PER_SM
 #define ANDI_FAST_BLOCKS_PER_SM 4
 #endif
-__global__ void __launch_bounds__(ANDI_WALK_THREADS, ANDI_FAST_BLOCKS_PER_SM)
+template <bool QUARTER>
+__global__ void __launch_bounds__(ANDI_WALK_THREADS, QUARTER ? ANDI_FAST_BLOCKS_PER_SM : ANDI_FAST_BLOCKS_PER_SM - 1)
 k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
 				   u32 nq, u32 chunk, u32 cpq, u32 threshold, u32 *__restrict__ records,
 				   unsigned long long *__restrict__ next_unit) {
@@ -135,7 +141,12 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 		if (op == OP_FETCH) {
 			op = OP_IDLE;
 			while (unit < total) {
-				u32 k = (u32)(unit / cpq), c = (u32)(unit % cpq);
+				u32 k, c;
+				if (total <= 0xffffffffULL) {  // 32-bit division: a fifth of the instructions
+					k = (u32)unit / cpq, c = (u32)unit - k * cpq;
+				} else {
+					k = (u32)(unit / cpq), c = (u32)(unit % cpq);
+				}
 				u32 qid = query_ids ? query_ids[k] : k;
 				u32 ql = queries[qid].t.len;
 				unsigned long long start = (unsigned long long)c * chunk;
@@ -275,12 +286,31 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 				u32 end_s = a_ls + a_ll, end_q = a_lq + a_ll;
 				bool pairs = R.s > end_s && (a_pos - end_q) == (R.s - end_s) && ((R.s < border) == (a_ls < border));
 				bool count_last = pairs || (a_pm & 1u) || a_ll >= 2u * t;
-				if (count_last) {  // model.c:247-254
+				if (count_last && QUARTER) {  // model.c:247-254
 					u32 f = (a_ll >> 2) * sign;
 					col[0 * ANDI_WALK_THREADS] += f;
 					col[5 * ANDI_WALK_THREADS] += f;
 					col[10 * ANDI_WALK_THREADS] += f;
 					col[15 * ANDI_WALK_THREADS] += f + (a_ll & 3u) * sign;
+				}
+				if (count_last && !QUARTER) {
+					// model.c:259-278: composition of the query slice [a_lq, a_lq + a_ll), in O(1)
+					// from the per-word prefix composition of the pool (k_comp_prefix): two table
+					// entries and the two partial words at the slice ends, one memory round.
+					const uint4 *cp = S.qcomp_base + (q_code - S.qcode_base);
+					u32 b0 = a_lq, b1 = a_lq + a_ll;
+					uint4 p0 = __ldg(cp + (b0 >> 5)), p1 = __ldg(cp + (b1 >> 5));
+					u64 w0 = __ldg(q_code + (b0 >> 5)), w1 = __ldg(q_code + (b1 >> 5));
+					u64 m0 = ANDI_EVEN_BITS & ((1ULL << (2u * (b0 & 31u))) - 1ULL);
+					u64 m1 = ANDI_EVEN_BITS & ((1ULL << (2u * (b1 & 31u))) - 1ULL);
+					u64 l0 = w0 & m0, h0 = (w0 >> 1) & m0, l1 = w1 & m1, h1 = (w1 >> 1) & m1;
+					u32 nc = p1.y - p0.y + (u32)__popcll(l1 & ~h1) - (u32)__popcll(l0 & ~h0);
+					u32 ng = p1.z - p0.z + (u32)__popcll(h1 & ~l1) - (u32)__popcll(h0 & ~l0);
+					u32 nt = p1.w - p0.w + (u32)__popcll(h1 & l1) - (u32)__popcll(h0 & l0);
+					col[0 * ANDI_WALK_THREADS] += (a_ll - nc - ng - nt) * sign;
+					col[5 * ANDI_WALK_THREADS] += nc * sign;
+					col[10 * ANDI_WALK_THREADS] += ng * sign;
+					col[15 * ANDI_WALK_THREADS] += nt * sign;
 				}
 				if (pairs) {
 					u32 g = a_pos - end_q;

@@ -48,17 +48,38 @@ static WalkPlan plan_walk(const andi_ctx *ctx, const std::vector<size_t> &qlens)
 	return p;
 }
 
-// Walk nq queries against one index; d_out gets nq cells of 17 words.
-static int launch_walk(andi_ctx *ctx, const SubjectIndex &S, const QueryView *d_queries, const u32 *d_query_ids,
-					   u32 nq, const WalkPlan &plan, u32 threshold, int model, bool spec, u32 *d_records,
-					   u32 *d_out) {
+// The pool's prefix-composition table (k_comp_prefix), built on first use.
+static int pool_comp_ensure(andi_ctx *ctx) {
+	if (ctx->pool_comp || !ctx->n) return ANDI_OK;
+	CK(dalloc(ctx, &ctx->pool_comp, ctx->pool_words));
+	k_comp_prefix<<<(unsigned)ctx->n, 256, 0, ctx->stream>>>(ctx->d_queries, ctx->pool_code, ctx->pool_comp);
+	ctx->st.esa_launches++;
+	CK(cudaGetLastError());
+	return ANDI_OK;
+}
+
+// Walk nq queries against one index; d_out gets nq cells of 17 words. `pool_queries`: the
+// query views are the pool's own (ctx->d_queries), so the prefix-composition table applies.
+static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries, const u32 *d_query_ids,
+					   u32 nq, const WalkPlan &plan, u32 threshold, int model, bool spec, bool pool_queries,
+					   u32 *d_records, u32 *d_out) {
 	chunks_fn cf = nullptr;
 	reduce_fn rf = nullptr;
 	pick_walk(model, spec, cf, rf);
-	// headline configuration (RAW/JC/KIMURA counting, no separators): the micro-op kernel
+	// no separators anywhere: the phase-pipeline kernel (headline: RAW/JC/KIMURA counting;
+	// LOGDET/ANI need the composition table, which only pool queries have)
 	const char *force = getenv("ANDI_B200_WALK");
 	bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
-	if (quarter && !spec && !(force && strcmp(force, "basic") == 0)) cf = k_walk_chunks_fast;
+	if (!spec && !(force && strcmp(force, "basic") == 0)) {
+		if (quarter) {
+			cf = k_walk_chunks_fast<true>;
+		} else if (pool_queries) {
+			int rc = pool_comp_ensure(ctx);
+			if (rc) return rc;
+			S.qcode_base = ctx->pool_code, S.qcomp_base = ctx->pool_comp;
+			cf = k_walk_chunks_fast<false>;
+		}
+	}
 	int per_sm = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf, ANDI_WALK_THREADS, 0));
 	if (per_sm < 1) per_sm = 1;
@@ -110,7 +131,7 @@ extern "C" int andi_dist_row(andi_ctx *ctx, const andi_esa *E, const size_t *que
 	CK(dalloc(ctx, &d_out, nq * 17));
 	CK(dalloc(ctx, &d_rec, plan.record_words));
 	CK(cudaMemcpyAsync(d_ids, ids.data(), nq * 4, cudaMemcpyHostToDevice, ctx->stream));
-	int rc = launch_walk(ctx, S, ctx->d_queries, d_ids, (u32)nq, plan, (u32)threshold, model, spec, d_rec, d_out);
+	int rc = launch_walk(ctx, S, ctx->d_queries, d_ids, (u32)nq, plan, (u32)threshold, model, spec, true, d_rec, d_out);
 	if (!rc) {
 		CK(cudaMemcpyAsync(out, d_out, nq * sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
@@ -140,7 +161,7 @@ extern "C" int andi_dist_anchor(andi_ctx *ctx, const andi_esa *E, const char *qu
 	u32 *d_out = nullptr, *d_rec = nullptr;
 	CK(dalloc(ctx, &d_out, 17));
 	CK(dalloc(ctx, &d_rec, plan.record_words));
-	rc = launch_walk(ctx, S, T.d_views, nullptr, 1, plan, (u32)threshold, model, E->has_sep || T.any_sep, d_rec, d_out);
+	rc = launch_walk(ctx, S, T.d_views, nullptr, 1, plan, (u32)threshold, model, E->has_sep || T.any_sep, false, d_rec, d_out);
 	if (!rc) {
 		CK(cudaMemcpyAsync(out, d_out, sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
@@ -188,7 +209,7 @@ static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_
 		if (!rc) {
 			SubjectIndex S = subject_index(&E);
 			rc = launch_walk(ctx, S, ctx->d_queries, nullptr, (u32)n, plan, E.threshold, model,
-							 ctx->any_sep || E.has_sep, d_rec, d_out + (i - s_begin) * n * 17);
+							 ctx->any_sep || E.has_sep, true, d_rec, d_out + (i - s_begin) * n * 17);
 		}
 	}
 	esa_release(&E);

@@ -36,6 +36,10 @@ struct SubjectIndex {
 	u32 threshold;		   // minimum anchor length for this subject
 	u32 self;			   // pool index of the subject (its own query is skipped)
 	u32 has_sep;		   // RS contains '!' / ';'
+	// query side, LOGDET / ANI fast path only: base of the pool's code plane and of its
+	// prefix-composition table (same word geometry), so comp = qcomp_base + (code - qcode_base)
+	const u64 *qcode_base;
+	const uint4 *qcomp_base;
 };
 
 struct QueryView {
@@ -206,6 +210,51 @@ __device__ __forceinline__ void count_anchor(Acc &M, const TextView &q, u32 pq, 
 		t += __popcll(hi & lo & valid);
 	}
 	M.add(0, a), M.add(5, c), M.add(10, g), M.add(15, t);
+}
+
+// ---- prefix composition of the pool (LOGDET / ANI fast path): entry j of a sequence holds the
+// number of A, C, G, T among its first 32*j bases, so the composition of any slice
+// (src/model.c:259-278 counts an anchor by its characters) is two entries plus two partial
+// words. One block per sequence, tiles of blockDim words with a running carry. Only valid for
+// sequences without separators (the fast kernels are not used otherwise).
+__global__ void __launch_bounds__(256) k_comp_prefix(const QueryView *__restrict__ queries,
+													 const u64 *__restrict__ pool_code, uint4 *__restrict__ pool_comp) {
+	const u64 *code = queries[blockIdx.x].t.code;
+	const u32 len = queries[blockIdx.x].t.len, entries = (len >> 5) + 1;
+	uint4 *out = pool_comp + (code - pool_code);
+	__shared__ uint4 warp_sum[8];
+	const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	uint4 carry = make_uint4(0, 0, 0, 0);
+	for (u32 base = 0; base < entries; base += blockDim.x) {
+		u32 j = base + threadIdx.x;
+		uint4 v = make_uint4(0, 0, 0, 0);
+		if (j < entries) {
+			u32 nb = min(32u, len - 32u * j);
+			u64 valid = nb == 32u ? ANDI_EVEN_BITS : (ANDI_EVEN_BITS & ((1ULL << (2u * nb)) - 1ULL));
+			u64 w = code[j], lo = w & valid, hi = (w >> 1) & valid;
+			v.y = (u32)__popcll(lo & ~hi), v.z = (u32)__popcll(hi & ~lo), v.w = (u32)__popcll(hi & lo);
+			v.x = nb - v.y - v.z - v.w;
+		}
+		uint4 inc = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			u32 x = __shfl_up_sync(0xffffffffu, inc.x, d), y = __shfl_up_sync(0xffffffffu, inc.y, d);
+			u32 z = __shfl_up_sync(0xffffffffu, inc.z, d), w = __shfl_up_sync(0xffffffffu, inc.w, d);
+			if (lane >= (u32)d) inc.x += x, inc.y += y, inc.z += z, inc.w += w;
+		}
+		if (lane == 31u) warp_sum[wid] = inc;
+		__syncthreads();
+		uint4 pre = carry, tot = carry;
+		for (u32 k = 0; k < 8; k++) {
+			uint4 ws = warp_sum[k];
+			if (k < wid) pre.x += ws.x, pre.y += ws.y, pre.z += ws.z, pre.w += ws.w;
+			tot.x += ws.x, tot.y += ws.y, tot.z += ws.z, tot.w += ws.w;
+		}
+		if (j < entries)
+			out[j] = make_uint4(pre.x + inc.x - v.x, pre.y + inc.y - v.y, pre.z + inc.z - v.z, pre.w + inc.w - v.w);
+		carry = tot;
+		__syncthreads();
+	}
 }
 
 // ---- the state that carries across iterations of the loop at src/process.c:153-197
