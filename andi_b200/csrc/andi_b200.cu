@@ -39,6 +39,7 @@ struct andi_ctx {
 	u64 *pool_code = nullptr, *pool_spec = nullptr;
 	size_t pool_words = 0;
 	uint4 *pool_comp = nullptr;	 // prefix composition per word, built on first LOGDET / ANI use
+	unsigned char *pool_sep3 = nullptr;	 // separator hints per word, built on first join-mode walk
 	QueryView *d_queries = nullptr;
 	bool any_sep = false;
 
@@ -49,6 +50,13 @@ struct andi_ctx {
 		unsigned char *amb = nullptr;
 		void *scan_tmp = nullptr;
 		size_t scan_bytes = 0, kmers_cap = 0, n_cap = 0;
+		// padded-suffix list of texts with separators (sa_bucket.cuh), double-buffered for the sort
+		u64 *pl_key[2] = {nullptr, nullptr};
+		u32 *pl_idx[2] = {nullptr, nullptr};
+		void *pl_tmp = nullptr;
+		size_t pl_tmp_bytes = 0, pl_cap = 0;
+		u32 *fvalid = nullptr;	// radix path only
+		size_t fvalid_cap = 0;
 	} bs;
 
 	unsigned long long *walk_counter = nullptr;  // unit dispenser of the walk kernels
@@ -63,6 +71,7 @@ struct andi_esa {
 	andi_ctx *ctx = nullptr;
 	u32 n = 0, N = 0;
 	u64 *code = nullptr, *spec = nullptr;
+	unsigned char *sep3 = nullptr;	// separator hints of the RS planes (k_sep3), has_sep only
 	u32 *SA = nullptr;
 	int32_t *LCP = nullptr;
 	u64 *dir = nullptr;
@@ -180,6 +189,7 @@ static void pool_release(andi_ctx *ctx) {
 	dfree(ctx, ctx->pool_code);
 	dfree(ctx, ctx->pool_spec);
 	dfree(ctx, ctx->pool_comp);
+	dfree(ctx, ctx->pool_sep3);
 	dfree(ctx, ctx->d_queries);
 	ctx->n = 0;
 	ctx->len.clear(), ctx->gc.clear(), ctx->has_sep.clear(), ctx->word_off.clear();
@@ -194,6 +204,9 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	pool_release(ctx);
 	dfree(ctx, ctx->bs.hist), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
 	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter);
+	dfree(ctx, ctx->bs.pl_key[0]), dfree(ctx, ctx->bs.pl_key[1]), dfree(ctx, ctx->bs.pl_idx[0]), dfree(ctx, ctx->bs.pl_idx[1]);
+	dfree(ctx, ctx->bs.fvalid);
+	if (ctx->bs.pl_tmp) cudaFreeAsync(ctx->bs.pl_tmp, ctx->stream);
 	if (ctx->bs.scan_tmp) cudaFreeAsync(ctx->bs.scan_tmp, ctx->stream);
 	cudaStreamSynchronize(ctx->stream);
 	for (auto e : ctx->free_ev) cudaEventDestroy(e);
@@ -447,7 +460,7 @@ extern "C" int andi_esa_build_rs(andi_ctx *ctx, const char *rs, size_t rs_len, u
 	unsigned long long cnt[2] = {0, 0};
 	cudaError_t e = cudaSuccess;
 	if ((e = dalloc(ctx, &E->code, nw)) != cudaSuccess || (e = dalloc(ctx, &E->spec, nw)) != cudaSuccess ||
-		(e = dalloc(ctx, &d_chars, rs_len)) != cudaSuccess || (e = dalloc(ctx, &d_cnt, 2)) != cudaSuccess) {
+		(e = dalloc(ctx, &E->sep3, nw)) != cudaSuccess || (e = dalloc(ctx, &d_chars, rs_len)) != cudaSuccess || (e = dalloc(ctx, &d_cnt, 2)) != cudaSuccess) {
 		ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(e);
 		esa_release(E);
 		delete E;
@@ -523,13 +536,15 @@ static SubjectIndex subject_index(const andi_esa *E) {
 	S.rs = rs_view(E);
 	S.SA = E->SA, S.LCP = E->LCP, S.dir = E->dir, S.plen = E->plen;
 	S.K = E->K, S.threshold = E->threshold, S.self = E->self, S.has_sep = E->has_sep;
-	S.qcode_base = nullptr, S.qcomp_base = nullptr;
+	S.qcode_base = nullptr, S.qcomp_base = nullptr, S.qspec_delta = 0;
+	S.s_sep3 = E->sep3, S.qsep3_base = nullptr;
 	return S;
 }
 
 // Upload + pack a list of host strings as temporary queries.
 struct TempQueries {
 	u64 *code = nullptr, *spec = nullptr;
+	unsigned char *sep3 = nullptr;
 	QueryView *d_views = nullptr;
 	bool any_sep = false;
 };
@@ -574,6 +589,7 @@ static int temp_queries(andi_ctx *ctx, const char *const *qs, const size_t *lens
 	CK(dalloc(ctx, &d_cnt, 2));
 	CK(dalloc(ctx, &T.code, words));
 	CK(dalloc(ctx, &T.spec, words));
+	CK(dalloc(ctx, &T.sep3, words));
 	CK(dalloc(ctx, &T.d_views, nq));
 	CK(cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
 	std::vector<QueryView> qv(nq);
@@ -610,6 +626,7 @@ static int temp_queries(andi_ctx *ctx, const char *const *qs, const size_t *lens
 		CK(cudaStreamSynchronize(ctx->stream));	 // host staging buffers go out of scope
 		dfree(ctx, d_coff), dfree(ctx, d_woff), dfree(ctx, d_len);
 	}
+	k_sep3<<<nblocks(words, 256), 256, 0, ctx->stream>>>(T.spec, words, T.sep3);
 	ctx->st.h2d_bytes += chars;
 	unsigned long long cnt[2];
 	CK(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -621,7 +638,7 @@ static int temp_queries(andi_ctx *ctx, const char *const *qs, const size_t *lens
 }
 
 static void temp_release(andi_ctx *ctx, TempQueries &T) {
-	dfree(ctx, T.code), dfree(ctx, T.spec), dfree(ctx, T.d_views);
+	dfree(ctx, T.code), dfree(ctx, T.spec), dfree(ctx, T.sep3), dfree(ctx, T.d_views);
 }
 
 extern "C" int andi_esa_get_match(const andi_esa *E, const char *const *queries, const size_t *lens, size_t nq,

@@ -214,7 +214,7 @@ static int build_full(andi_ctx *ctx, andi_esa *E) {
 
 static void esa_release(andi_esa *E) {
 	andi_ctx *ctx = E->ctx;
-	dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->SA), dfree(ctx, E->LCP);
+	dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->sep3), dfree(ctx, E->SA), dfree(ctx, E->LCP);
 	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->plen), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
 	dfree(ctx, E->cache);
 	E->cap_words = E->cap_n = E->cap_kmers = E->cap_present = 0;
@@ -225,9 +225,10 @@ static void esa_release(andi_esa *E) {
 static int esa_ensure(andi_ctx *ctx, andi_esa *E) {
 	const size_t nw = plane_words(E->N);
 	if (nw > E->cap_words) {
-		dfree(ctx, E->code), dfree(ctx, E->spec);
+		dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->sep3);
 		CK(dalloc(ctx, &E->code, nw));
 		CK(dalloc(ctx, &E->spec, nw));
+		CK(dalloc(ctx, &E->sep3, nw));
 		E->cap_words = nw;
 	}
 	if ((size_t)E->N > E->cap_n) {
@@ -257,7 +258,7 @@ static int esa_ensure(andi_ctx *ctx, andi_esa *E) {
 
 static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
 	auto &b = ctx->bs;
-	if (!b.flags) CK(dalloc(ctx, &b.flags, 2));
+	if (!b.flags) CK(dalloc(ctx, &b.flags, 4));
 	if (kmers > b.kmers_cap) {
 		dfree(ctx, b.hist), dfree(ctx, b.bstart);
 		if (b.scan_tmp) cudaFreeAsync(b.scan_tmp, ctx->stream);
@@ -278,6 +279,38 @@ static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
 	return ANDI_OK;
 }
 
+// The padded-suffix list (texts with separators), `cap` entries.
+static int padded_ensure(andi_ctx *ctx, size_t cap) {
+	auto &b = ctx->bs;
+	if (cap <= b.pl_cap) return ANDI_OK;
+	for (int x = 0; x < 2; x++) {
+		dfree(ctx, b.pl_key[x]), dfree(ctx, b.pl_idx[x]);
+		CK(dalloc(ctx, &b.pl_key[x], cap));
+		CK(dalloc(ctx, &b.pl_idx[x], cap));
+	}
+	if (b.pl_tmp) cudaFreeAsync(b.pl_tmp, ctx->stream);
+	b.pl_tmp = nullptr, b.pl_tmp_bytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, b.pl_tmp_bytes, b.pl_key[0], b.pl_key[1], b.pl_idx[0], b.pl_idx[1], (int)cap, 0, 63,
+									ctx->stream);
+	CK(cudaMallocAsync(&b.pl_tmp, b.pl_tmp_bytes, ctx->stream));
+	b.pl_cap = cap;
+	return ANDI_OK;
+}
+
+// Sort the padded list and write it to the bucket fronts.
+static int padded_finish(andi_ctx *ctx, andi_esa *E, const TextView &rs) {
+	auto &b = ctx->bs;
+	cudaStream_t st = ctx->stream;
+	const u32 cap = (u32)b.pl_cap;
+	CK(cub::DeviceRadixSort::SortPairs(b.pl_tmp, b.pl_tmp_bytes, b.pl_key[0], b.pl_key[1], b.pl_idx[0], b.pl_idx[1], (int)cap, 0,
+									   63, st));
+	k_padded_ties<true><<<nblocks(cap, 128), 128, 0, st>>>(rs, b.pl_key[1], b.pl_idx[1], b.flags + 2, cap);
+	k_padded_place<<<nblocks(cap, 128), 128, 0, st>>>(E->K, b.pl_key[1], b.pl_idx[1], b.flags + 2, cap, b.bstart, E->SA);
+	ctx->st.esa_launches += 2;
+	ctx->st.cub_calls += 1;
+	return ANDI_OK;
+}
+
 // Texts above this many characters bucket through the library radix sort (tables beyond L2).
 #define ANDI_BUCKET_ATOMIC_MAX (8u << 20)
 
@@ -290,16 +323,37 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 	int rc = scratch_ensure(ctx, kmers, N);
 	if (rc) return rc;
 	auto &b = ctx->bs;
-	CK(cudaMemsetAsync(b.flags, 0, 2 * sizeof(u32), st));
+	const bool sep = E->has_sep;
+	const u32 *fvalid = nullptr, *bend = nullptr;
+	if (sep && b.pl_cap == 0) {
+		rc = padded_ensure(ctx, (size_t)1 << 16);
+		if (rc) return rc;
+	}
+rebuild:
+	CK(cudaMemsetAsync(b.flags, 0, 4 * sizeof(u32), st));
+	PaddedList pl{b.pl_key[0], b.pl_idx[0], b.flags + 2, (u32)b.pl_cap};
+	if (sep) {	// unused list slots sort to the end
+		CK(cudaMemsetAsync(b.pl_key[0], 0xff, b.pl_cap * sizeof(u64), st));
+		CK(cudaMemsetAsync(b.pl_idx[0], 0xff, b.pl_cap * sizeof(u32), st));
+	}
 	if (N <= ANDI_BUCKET_ATOMIC_MAX) {
 		// counting sort with L2-resident tables: histogram, scan, scatter
 		CK(cudaMemsetAsync(b.hist, 0, (kmers + 1) * sizeof(u32), st));
 		k_bucket_hist<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist);
 		size_t sb = b.scan_bytes;
 		CK(cub::DeviceScan::ExclusiveSum(b.scan_tmp, sb, b.hist, b.bstart, (int)(kmers + 1), st));
-		// the histogram becomes the scatter cursor: after the scatter hist[key] = end of bucket key
-		CK(cudaMemcpyAsync(b.hist, b.bstart, kmers * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-		k_bucket_scatter<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist, E->SA);
+		if (!sep) {
+			// the histogram becomes the scatter cursor: after the scatter hist[key] = end of bucket key
+			CK(cudaMemcpyAsync(b.hist, b.bstart, kmers * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+			k_bucket_scatter<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist, E->SA);
+			bend = b.hist;
+		} else {
+			// valid suffixes fill their bucket from the back: the cursor starts at the bucket end and
+			// stops at the first valid one; the padded ones go through the list to the front
+			CK(cudaMemcpyAsync(b.hist, b.bstart + 1, kmers * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+			k_bucket_scatter_spec<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist, E->SA, pl);
+			bend = b.bstart + 1, fvalid = b.hist;
+		}
 		ctx->st.esa_launches += 2;
 		ctx->st.cub_calls += 1;
 	} else {
@@ -308,40 +362,69 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 		CK(dalloc(ctx, &keys_a, N));
 		CK(dalloc(ctx, &keys_b, N));
 		CK(dalloc(ctx, &idx, N));
+		const int bits = 2 * K + (sep ? 1 : 0);
 		size_t sort_bytes = 0;
-		cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_a, keys_b, idx, E->SA, (int)N, 0, 2 * K, st);
+		cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_a, keys_b, idx, E->SA, (int)N, 0, bits, st);
 		void *tmp = nullptr;
 		CK(cudaMallocAsync(&tmp, sort_bytes, st));
-		k_bucket_keys<<<nblocks(N, 256), 256, 0, st>>>(rs, K, keys_a, idx);
-		CK(cub::DeviceRadixSort::SortPairs(tmp, sort_bytes, keys_a, keys_b, idx, E->SA, (int)N, 0, 2 * K, st));
+		if (sep)
+			k_bucket_keys_spec<<<nblocks(N, 256), 256, 0, st>>>(rs, K, keys_a, idx, pl);
+		else
+			k_bucket_keys<<<nblocks(N, 256), 256, 0, st>>>(rs, K, keys_a, idx);
+		CK(cub::DeviceRadixSort::SortPairs(tmp, sort_bytes, keys_a, keys_b, idx, E->SA, (int)N, 0, bits, st));
 		CK(cudaMemsetAsync(b.bstart, 0, kmers * sizeof(u32), st));
 		CK(cudaMemsetAsync(b.hist, 0, kmers * sizeof(u32), st));
-		k_bucket_bounds<<<nblocks(N, 256), 256, 0, st>>>(keys_b, N, b.bstart, b.hist);
+		if (sep) {
+			if (kmers > b.fvalid_cap) {
+				dfree(ctx, b.fvalid);
+				CK(dalloc(ctx, &b.fvalid, kmers));
+				b.fvalid_cap = kmers;
+			}
+			CK(cudaMemsetAsync(b.fvalid, 0, kmers * sizeof(u32), st));
+			k_bucket_bounds_spec<<<nblocks(N, 256), 256, 0, st>>>(keys_b, N, b.bstart, b.hist, b.fvalid);
+			fvalid = b.fvalid;
+		} else {
+			k_bucket_bounds<<<nblocks(N, 256), 256, 0, st>>>(keys_b, N, b.bstart, b.hist);
+		}
+		bend = b.hist;
 		cudaFreeAsync(tmp, st);
 		dfree(ctx, keys_a), dfree(ctx, keys_b), dfree(ctx, idx);
 		ctx->st.esa_launches += 2;
 		ctx->st.cub_calls += 1;
 	}
-	if (E->has_sep) {
-		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, E->dir, b.flags);
+	if (sep) {
+		rc = padded_finish(ctx, E, rs);
+		if (rc) return rc;
+		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags);
 		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	} else {
-		k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, E->dir, b.flags);
+		k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, E->dir, b.flags);
 		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	}
 	ctx->st.esa_launches += 2;
 	rc = build_prefix_lengths(ctx, E);
-	u32 h_flags[2] = {0, 0};
+	u32 h_flags[4] = {0, 0, 0, 0};
 	if (!rc) {
 		CK(cudaMemcpyAsync(h_flags, b.flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 	}
+	if (!rc && sep && h_flags[2] > b.pl_cap) {
+		// more padded suffixes than the list held: grow it and build again (first subject only, as a rule)
+		size_t want = (size_t)h_flags[2] * 2;
+		if (want > (size_t)INT_MAX) {
+			ctx->err = "too many separators";
+			return ANDI_ERR_TOO_LONG;
+		}
+		rc = padded_ensure(ctx, want);
+		if (rc) return rc;
+		goto rebuild;
+	}
 	if (!rc && h_flags[0]) {
 		// tied suffixes: materialise their groups, refine them, then take the LCP again
 		if (E->has_sep)
-			k_bucket_groups<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, b.grp, b.rank, b.amb);
+			k_bucket_groups<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, b.grp, b.rank, b.amb);
 		else
-			k_bucket_groups<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, b.hist, E->SA, b.grp, b.rank, b.amb);
+			k_bucket_groups<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, b.grp, b.rank, b.amb);
 		ctx->st.esa_launches++;
 		rc = doubling_rounds(ctx, E, b.grp, b.rank, b.amb, (u32)K);
 		if (!rc) {
@@ -351,7 +434,7 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 			else
 				k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 			ctx->st.esa_launches++;
-			CK(cudaMemcpyAsync(h_flags, b.flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(h_flags, b.flags, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
 		}
 	}
@@ -369,6 +452,11 @@ static int build_index(andi_ctx *ctx, andi_esa *E, unsigned flags) {
 	}
 	int rc = esa_ensure(ctx, E);
 	if (rc) return rc;
+	{  // separator hints for a join-mode walk (the queries may hold separators even if RS has only '#')
+		const size_t nw = plane_words(E->N);
+		k_sep3<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(E->spec, nw, E->sep3);
+		ctx->st.esa_launches++;
+	}
 	if (E->K >= 2) {
 		rc = build_index_bucket(ctx, E);
 	} else {

@@ -92,17 +92,153 @@ __global__ void k_bucket_bounds(const u32 *__restrict__ keys, u32 N, u32 *__rest
 	if (j + 1 == N || keys[j + 1] != k) bend[k] = j + 1;
 }
 
+// ---- texts with separators ('!' / ';' of join mode): the padded suffixes.
+// Every suffix with a separator (or the text end) inside its first K characters has a padded
+// key, and they pile up: all suffixes that START with a separator share key 0, a genome of
+// 2000 contigs puts ~5000 suffixes there. They are therefore kept out of the per-bucket
+// insertion sort: the bucketing pass appends them to a list with an order-preserving 63-bit
+// key (the byte-order ranks of their first 21 characters, 3 bits each), the list is sorted by
+// a library radix sort, the rare equal keys are settled by direct comparison, and every padded
+// suffix is written to the FRONT of its bucket (the padded key is monotone, so the sorted list
+// restricted to a bucket is the bucket's order). The valid suffixes fill the bucket from the
+// back; fvalid[key] = index of the first valid one.
+struct PaddedList {
+	u64 *key;
+	u32 *idx;
+	u32 *count;	 // appended so far (may exceed cap: the host then grows the list and rebuilds)
+	u32 cap;
+};
+
+__device__ __forceinline__ u64 order_key21(const TextView &rs, u32 p) {
+	u64 cw = window32(rs.code, p), sw = window32(rs.spec, p);
+	u32 left = rs.len - p;
+	u64 key = 0;
+#pragma unroll
+	for (u32 c = 0; c < 21; c++) {
+		u32 code = (u32)(cw >> (2 * c)) & 3u, sp = (u32)(sw >> (2 * c)) & 1u;
+		u32 r = c < left ? (sp ? code + 1u : code + 4u) : 0u;
+		key = (key << 3) | r;
+	}
+	return key;
+}
+
+// The padded bucket key of a suffix from its order key (K <= 14 < 21): codes up to the first
+// separator / end, zeros from there.
+__device__ __forceinline__ u32 bucket_of_order_key(u64 key21, int K) {
+	u32 out = 0;
+	bool open = true;
+	for (int c = 0; c < K; c++) {
+		u32 r = (u32)(key21 >> (3 * (20 - c))) & 7u;
+		open = open && r >= 4u;
+		out = (out << 2) | (open ? r - 4u : 0u);
+	}
+	return out;
+}
+
+__device__ __forceinline__ void padded_append(const PaddedList &pl, const TextView &rs, u32 p) {
+	u32 slot = atomicAdd(pl.count, 1u);
+	if (slot < pl.cap) pl.key[slot] = order_key21(rs, p), pl.idx[slot] = p;
+}
+
+// Scatter of the counting-sort path: valid suffixes fill their bucket from the back
+// (cursor_end starts at the bucket end and ends at fvalid), padded ones go to the list.
+__global__ void k_bucket_scatter_spec(TextView rs, int K, u32 *__restrict__ cursor_end, u32 *__restrict__ SA,
+									  PaddedList pl) {
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= rs.len) return;
+	u32 run;
+	u32 key = padded_key(rs, i, K, run);
+	if (run < (u32)K)
+		padded_append(pl, rs, i);
+	else
+		SA[atomicSub(cursor_end + key, 1u) - 1u] = i;
+}
+
+// Radix-sort path: sort key = bucket key * 2 + valid, so the padded suffixes come first.
+__global__ void k_bucket_keys_spec(TextView rs, int K, u32 *__restrict__ keys, u32 *__restrict__ idx, PaddedList pl) {
+	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= rs.len) return;
+	u32 run;
+	u32 key = padded_key(rs, i, K, run);
+	bool valid = run >= (u32)K;
+	if (!valid) padded_append(pl, rs, i);
+	keys[i] = (key << 1) | (valid ? 1u : 0u);
+	idx[i] = i;
+}
+
+__global__ void k_bucket_bounds_spec(const u32 *__restrict__ keys, u32 N, u32 *__restrict__ bstart,
+									 u32 *__restrict__ bend, u32 *__restrict__ fvalid) {
+	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= N) return;
+	u32 kv = keys[j], k = kv >> 1;
+	bool first_of_run = j == 0 || keys[j - 1] != kv, last_of_run = j + 1 == N || keys[j + 1] != kv;
+	if (j == 0 || (keys[j - 1] >> 1) != k) bstart[k] = j;
+	if (j + 1 == N || (keys[j + 1] >> 1) != k) bend[k] = j + 1;
+	if ((kv & 1u) && first_of_run) fvalid[k] = j;
+	if (!(kv & 1u) && last_of_run) fvalid[k] = j + 1;
+}
+
+// Equal order keys (two padded suffixes agreeing on 21 characters: duplicated contig starts):
+// the thread at the head of such a run orders it by direct comparison.
+template <bool SPEC>
+__global__ void k_padded_ties(TextView rs, const u64 *__restrict__ key, u32 *__restrict__ idx,
+							  const u32 *__restrict__ count, u32 cap) {
+	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 P = min(*count, cap);
+	if (j >= P) return;
+	u64 k = key[j];
+	if (j > 0 && key[j - 1] == k) return;
+	u32 e = j + 1;
+	while (e < P && key[e] == k) e++;
+	for (u32 x = j + 1; x < e; x++) {
+		u32 cur = idx[x];
+		u32 y = x;
+		while (y > j && compare_suffixes<SPEC>(rs, idx[y - 1], cur, 0xffffffffu) > 0) {
+			idx[y] = idx[y - 1];
+			y--;
+		}
+		idx[y] = cur;
+	}
+}
+
+// Sorted padded suffix j goes to slot (j - first list index of its bucket) of its bucket.
+__global__ void k_padded_place(int K, const u64 *__restrict__ key, const u32 *__restrict__ idx,
+							   const u32 *__restrict__ count, u32 cap, const u32 *__restrict__ bstart,
+							   u32 *__restrict__ SA) {
+	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 P = min(*count, cap);
+	if (j >= P) return;
+	u32 bk = bucket_of_order_key(key[j], K);
+	u32 lo = 0, hi = j;
+	while (lo < hi) {
+		u32 m = lo + ((hi - lo) >> 1);
+		if (bucket_of_order_key(key[m], K) < bk)
+			lo = m + 1;
+		else
+			hi = m;
+	}
+	SA[bstart[bk] + (j - lo)] = idx[j];
+}
+
 // dir64[key] = first SA index of the suffixes that really start with this k-mer (no
 // separator inside) | their number << 32. *n_ambiguous counts the suffixes that are still tied
 // with a neighbour; their groups are materialised by k_bucket_groups only when there are any.
 template <bool SPEC>
 __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
-							  u32 *__restrict__ SA, u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous) {
+							  const u32 *__restrict__ fvalid, u32 *__restrict__ SA, u64 *__restrict__ dir64,
+							  u32 *__restrict__ n_ambiguous) {
 	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
 	if (key >= (1u << (2 * K))) return;
-	const u32 b = bstart[key], e = bend[key], s = e - b;
-	if (s == 0) {
+	const u32 e = bend[key];
+	// fvalid given: the padded suffixes already stand sorted in [bstart, fvalid) (k_padded_place)
+	const u32 b = fvalid ? min(fvalid[key], e) : bstart[key], s = e - b;
+	if (e == bstart[key]) {
 		dir64[key] = 0;
+		return;
+	}
+	if (fvalid && s > ANDI_SORT_MAX) {	// valid suffixes only: one group of depth K for the doubling rounds
+		atomicAdd(n_ambiguous, s);
+		dir64[key] = (u64)b | ((u64)s << 32);
 		return;
 	}
 	u32 valid = 0;
@@ -150,7 +286,7 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 	u32 tied = 0;
 	for (u32 x = 0; x < s; x++) {
 		u32 p = v[x];
-		valid += !is_padded<SPEC>(rs, p, K);
+		valid += fvalid ? 1u : (u32)!is_padded<SPEC>(rs, p, K);
 		if (s > 1) SA[b + x] = p;
 		if (x > 0 && compare_suffixes<SPEC>(rs, v[x - 1], p, ANDI_SORT_CAP) == 0) tied++;
 	}
@@ -163,15 +299,23 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 // k_bucket_sort left them.
 template <bool SPEC>
 __global__ void k_bucket_groups(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
-								const u32 *__restrict__ SA, u32 *__restrict__ grp, u32 *__restrict__ rank,
-								unsigned char *__restrict__ amb) {
+								const u32 *__restrict__ fvalid, const u32 *__restrict__ SA, u32 *__restrict__ grp,
+								u32 *__restrict__ rank, unsigned char *__restrict__ amb) {
 	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
 	if (key >= (1u << (2 * K))) return;
-	const u32 b = bstart[key], e = bend[key], s = e - b;
-	if (s == 0) return;
+	u32 b = bstart[key];
+	const u32 e = bend[key];
+	if (e == b) return;
+	if (fvalid) {  // sorted padded suffixes in front: singleton groups
+		u32 f = min(fvalid[key], e);
+		for (u32 j = b; j < f; j++) grp[j] = j, rank[SA[j]] = j, amb[j] = 0;
+		b = f;
+		if (e == b) return;
+	}
+	const u32 s = e - b;
 	if (s > ANDI_SORT_MAX) {
 		u32 front = b;
-		for (; front < e; front++) {
+		for (; front < e && !fvalid; front++) {
 			if (!is_padded<SPEC>(rs, SA[front], K)) break;
 		}
 		for (u32 j = b; j < front; j++) grp[j] = j, rank[SA[j]] = j, amb[j] = 0;

@@ -1,9 +1,10 @@
 // andi_b200/csrc/walk_fast.cuh -- k_walk_chunks_fast: the chunked anchor walk of
 // walk_kernels.cuh as a phase pipeline with carry-over.
 //
-// Same units, same records, same results as k_walk_chunks<QUARTER, SPEC=false> (no '!' in
-// subject or queries; QUARTER = RAW / JC / KIMURA counting is the headline configuration,
-// !QUARTER = LOGDET / ANI needs the pool's prefix-composition table). What changes
+// Same units, same records, same results as k_walk_chunks<QUARTER, SPEC>. QUARTER = RAW / JC /
+// KIMURA counting without separators is the headline configuration; !QUARTER (LOGDET / ANI)
+// needs the pool's prefix-composition table; SPEC (join mode, '!' in subject or queries) reads
+// the spec planes next to the code planes. What changes
 // is the execution shape. In the straightforward kernel every lane runs nested while-loops
 // (window compares of different lengths, bucket scans, bitmap probes) and the warp waits for
 // its slowest lane at every level: ncu showed 6 of 32 lanes active. A pure lane-level state
@@ -50,19 +51,39 @@ struct LaneResult {
 	u32 s, len, mm, found;
 };
 
+#define ANDI_KEY_SEP 0x80000000u  // L.key: a separator among the first K query characters (SPEC)
+
 // One 64-base window of the current compare; sets `op` when the compare has ended.
+// SPEC: bytes are equal when code pair and spec pair are equal (text.cuh); a column with a
+// separator on either side never becomes a remembered `mm` class (COLS skips such columns).
+template <bool SPEC>
 __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &L, LaneResult &R,
-										   const u64 *__restrict__ q_code, const u64 *__restrict__ s_code, u32 a_pos,
-										   u32 qlen, u32 t, int K) {
+										   const u64 *__restrict__ q_code, const u64 *__restrict__ q_spec,
+										   const u64 *__restrict__ s_code, const u64 *__restrict__ s_spec,
+										   const unsigned char *__restrict__ q_sep3, const unsigned char *__restrict__ s_sep3,
+										   u32 a_pos, u32 qlen, u32 t, int K) {
 	// plain window loads (three words = 64 bases per text): they hit L1/L2, and a register cache
 	// of the last words costs more instructions and registers than it saves (measured: +14 %
 	// throughput without it). 64 bases end 96 % of all compares in one pass.
+	// SPEC: one byte per text says whether any of the three words holds a separator (k_sep3);
+	// the spec planes are only read where it does
+	u32 sep_near = 0;
+	if (SPEC) sep_near = __ldg(q_sep3 + ((a_pos + C.ck) >> 5)) | __ldg(s_sep3 + ((C.cs + C.ck) >> 5));
 	u64 q0, q1, s0, s1;
 	window64(q_code, a_pos + C.ck, q0, q1);
 	window64(s_code, C.cs + C.ck, s0, s1);
 	if (C.ck == 0 && !C.is_cand) L.key = K > 0 ? kmer_key(q0, K) : 0u;
 	// first differing base of the window (a differing 2-bit code has its lowest set bit at 2d or 2d+1)
 	u64 x0 = q0 ^ s0, x1 = q1 ^ s1;
+	u64 sep0 = 0, sep1 = 0;
+	if (SPEC && sep_near) {
+		u64 qs0, qs1, ss0, ss1;
+		window64(q_spec, a_pos + C.ck, qs0, qs1);
+		window64(s_spec, C.cs + C.ck, ss0, ss1);
+		x0 |= qs0 ^ ss0, x1 |= qs1 ^ ss1;
+		sep0 = qs0 | ss0, sep1 = qs1 | ss1;
+		if (C.ck == 0 && !C.is_cand && K > 0 && (qs0 & ((1ULL << (2 * K)) - 1ULL))) L.key |= ANDI_KEY_SEP;
+	}
 	u32 left = C.clim - C.ck;
 	u32 d = x0 ? (u32)(__ffsll((long long)x0) - 1) >> 1 : (x1 ? 32u + ((u32)(__ffsll((long long)x1) - 1) >> 1) : 64u);
 	u32 len, mm = 0;
@@ -73,6 +94,7 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 		u64 sw = d < 32u ? s0 : s1, qw = d < 32u ? q0 : q1;
 		u32 sh = 2u * (d & 31u);
 		mm = ANDI_MM_VALID | ((((u32)(sw >> sh)) & 3u) << 2) | (((u32)(qw >> sh)) & 3u);
+		if (SPEC && (((d < 32u ? sep0 : sep1) >> sh) & 1ULL)) mm = 0;
 	} else {
 		C.ck += 64u;
 		return;	 // compare continues
@@ -81,7 +103,7 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 		if (len >= t) {
 			R.found = 1, R.s = C.cs, R.len = len, R.mm = mm;
 			op = OP_DECIDE;
-		} else if (K > 0 && qlen - a_pos >= (u32)K) {
+		} else if (K > 0 && qlen - a_pos >= (u32)K && !(SPEC && (L.key & ANDI_KEY_SEP))) {
 			op = OP_DIR;  // process.c:117: longest match anywhere in RS
 		} else {
 			op = OP_SLOW;
@@ -109,8 +131,8 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 #ifndef ANDI_FAST_BLOCKS_PER_SM
 #define ANDI_FAST_BLOCKS_PER_SM 4
 #endif
-template <bool QUARTER>
-__global__ void __launch_bounds__(ANDI_WALK_THREADS, QUARTER ? ANDI_FAST_BLOCKS_PER_SM : ANDI_FAST_BLOCKS_PER_SM - 1)
+template <bool QUARTER, bool SPEC>
+__global__ void __launch_bounds__(ANDI_WALK_THREADS, (QUARTER && !SPEC) ? ANDI_FAST_BLOCKS_PER_SM : ANDI_FAST_BLOCKS_PER_SM - 1)
 k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
 				   u32 nq, u32 chunk, u32 cpq, u32 threshold, u32 *__restrict__ records,
 				   unsigned long long *__restrict__ next_unit) {
@@ -122,6 +144,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 	const u32 t = threshold, N = S.rs.len, mid = S.rs.mid, border = N / 2;
 	const int K = S.K;
 	const u64 *__restrict__ s_code = S.rs.code;
+	const u64 *__restrict__ s_spec = S.rs.spec;
 
 	// ---- lane state
 	u32 op = OP_FETCH;
@@ -219,7 +242,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 				u32 guess = a_ls + advance;
 				if (guess < N && gap <= t) {
 					C.cs = guess;
-					u32 run = guess < mid ? mid - guess : (guess == mid ? 0u : N - guess);
+					u32 run = SPEC ? N - guess : (guess < mid ? mid - guess : (guess == mid ? 0u : N - guess));
 					C.clim = min(rem, run);
 				} else {
 					C.cs = 0, C.clim = 0;  // no lucky attempt: the window op only fetches the query k-mer
@@ -231,7 +254,8 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ CMP, first window of the trip
-		if (op == OP_CMP) cmp_window(op, C, L, R, q_code, s_code, a_pos, qlen, t, K);
+		if (op == OP_CMP) cmp_window<SPEC>(op, C, L, R, q_code, q_code + S.qspec_delta, s_code, s_spec,
+											   S.qsep3_base + (q_code - S.qcode_base), S.s_sep3, a_pos, qlen, t, K);
 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ DIR
@@ -256,21 +280,22 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 		// ------------------------------------------------------------ CAND
 		if (op == OP_CAND) {
 			u32 p = __ldg(S.SA + L.cand), rem = qlen - a_pos;
-			u32 run = p < mid ? mid - p : (p == mid ? 0u : N - p);
+			u32 run = SPEC ? N - p : (p < mid ? mid - p : (p == mid ? 0u : N - p));
 			C.cs = p, C.ck = 0, C.clim = min(rem, run), C.is_cand = 1;
 			op = OP_CMP;
 		}
 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ CMP, second window / candidate
-		if (op == OP_CMP) cmp_window(op, C, L, R, q_code, s_code, a_pos, qlen, t, K);
+		if (op == OP_CMP) cmp_window<SPEC>(op, C, L, R, q_code, q_code + S.qspec_delta, s_code, s_spec,
+											   S.qsep3_base + (q_code - S.qcode_base), S.s_sep3, a_pos, qlen, t, K);
 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ SLOW (rare)
 		if (op == OP_SLOW) {
 			TextView qv;
-			qv.code = q_code, qv.spec = nullptr, qv.len = qlen, qv.mid = 0xffffffffu;
-			MatchResult m = longest_match<false>(S, qv, a_pos, qlen - a_pos);
+			qv.code = q_code, qv.spec = SPEC ? q_code + S.qspec_delta : nullptr, qv.len = qlen, qv.mid = 0xffffffffu;
+			MatchResult m = longest_match<SPEC>(S, qv, a_pos, qlen - a_pos);
 			R.found = (m.unique && m.len >= t) ? 1u : 0u;
 			R.len = m.len, R.mm = 0;
 			R.s = R.found ? __ldg(S.SA + m.at) : 0u;
@@ -303,11 +328,16 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 					u64 w0 = __ldg(q_code + (b0 >> 5)), w1 = __ldg(q_code + (b1 >> 5));
 					u64 m0 = ANDI_EVEN_BITS & ((1ULL << (2u * (b0 & 31u))) - 1ULL);
 					u64 m1 = ANDI_EVEN_BITS & ((1ULL << (2u * (b1 & 31u))) - 1ULL);
+					if (SPEC) {	 // separators are not counted
+						m0 &= ~__ldg(q_code + S.qspec_delta + (b0 >> 5));
+						m1 &= ~__ldg(q_code + S.qspec_delta + (b1 >> 5));
+					}
 					u64 l0 = w0 & m0, h0 = (w0 >> 1) & m0, l1 = w1 & m1, h1 = (w1 >> 1) & m1;
+					u32 na = p1.x - p0.x + (u32)__popcll(m1 & ~l1 & ~h1) - (u32)__popcll(m0 & ~l0 & ~h0);
 					u32 nc = p1.y - p0.y + (u32)__popcll(l1 & ~h1) - (u32)__popcll(l0 & ~h0);
 					u32 ng = p1.z - p0.z + (u32)__popcll(h1 & ~l1) - (u32)__popcll(h0 & ~l0);
 					u32 nt = p1.w - p0.w + (u32)__popcll(h1 & l1) - (u32)__popcll(h0 & l0);
-					col[0 * ANDI_WALK_THREADS] += (a_ll - nc - ng - nt) * sign;
+					col[0 * ANDI_WALK_THREADS] += na * sign;
 					col[5 * ANDI_WALK_THREADS] += nc * sign;
 					col[10 * ANDI_WALK_THREADS] += ng * sign;
 					col[15 * ANDI_WALK_THREADS] += nt * sign;
@@ -336,6 +366,8 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 			u64 qw = window32(q_code, cols_q), sw = window32(s_code, cols_s);
 			u64 valid = span == 32u ? ANDI_EVEN_BITS : (ANDI_EVEN_BITS & ((1ULL << (2u * span)) - 1ULL));
 			if (cols_s <= mid && mid - cols_s < span) valid &= ~(1ULL << (2u * (mid - cols_s)));  // '#' column
+			if (SPEC && (__ldg(S.s_sep3 + (cols_s >> 5)) | __ldg(S.qsep3_base + (q_code - S.qcode_base) + (cols_q >> 5))))
+				valid &= ~(window32(s_spec, cols_s) | window32(q_code + S.qspec_delta, cols_q));
 			u64 x = qw ^ sw;
 			u64 neq = (x | (x >> 1)) & valid, eq = valid & ~neq;
 			u64 lo = qw & ANDI_EVEN_BITS, hb = (qw >> 1) & ANDI_EVEN_BITS;

@@ -58,6 +58,16 @@ static int pool_comp_ensure(andi_ctx *ctx) {
 	return ANDI_OK;
 }
 
+// The pool's separator hints (k_sep3), built on first use.
+static int pool_sep3_ensure(andi_ctx *ctx) {
+	if (ctx->pool_sep3 || !ctx->n) return ANDI_OK;
+	CK(dalloc(ctx, &ctx->pool_sep3, ctx->pool_words));
+	k_sep3<<<nblocks(ctx->pool_words, 256), 256, 0, ctx->stream>>>(ctx->pool_spec, ctx->pool_words, ctx->pool_sep3);
+	ctx->st.esa_launches++;
+	CK(cudaGetLastError());
+	return ANDI_OK;
+}
+
 // Walk nq queries against one index; d_out gets nq cells of 17 words. `pool_queries`: the
 // query views are the pool's own (ctx->d_queries), so the prefix-composition table applies.
 static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries, const u32 *d_query_ids,
@@ -66,18 +76,27 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	chunks_fn cf = nullptr;
 	reduce_fn rf = nullptr;
 	pick_walk(model, spec, cf, rf);
-	// no separators anywhere: the phase-pipeline kernel (headline: RAW/JC/KIMURA counting;
-	// LOGDET/ANI need the composition table, which only pool queries have)
+	// the phase-pipeline kernels (headline: RAW/JC/KIMURA counting without separators; LOGDET/ANI
+	// need the composition table, which only pool queries have)
 	const char *force = getenv("ANDI_B200_WALK");
 	bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
-	if (!spec && !(force && strcmp(force, "basic") == 0)) {
+	if (!(force && strcmp(force, "basic") == 0)) {
+		if (spec && pool_queries) {
+			int rc = pool_sep3_ensure(ctx);
+			if (rc) return rc;
+			S.qcode_base = ctx->pool_code, S.qsep3_base = ctx->pool_sep3;
+		}
+		if (spec && !S.s_sep3) {
+			ctx->err = "index without separator hints";
+			return ANDI_ERR_ARG;
+		}
 		if (quarter) {
-			cf = k_walk_chunks_fast<true>;
+			cf = spec ? k_walk_chunks_fast<true, true> : k_walk_chunks_fast<true, false>;
 		} else if (pool_queries) {
 			int rc = pool_comp_ensure(ctx);
 			if (rc) return rc;
 			S.qcode_base = ctx->pool_code, S.qcomp_base = ctx->pool_comp;
-			cf = k_walk_chunks_fast<false>;
+			cf = spec ? k_walk_chunks_fast<false, true> : k_walk_chunks_fast<false, false>;
 		}
 	}
 	int per_sm = 0;
@@ -124,6 +143,7 @@ extern "C" int andi_dist_row(andi_ctx *ctx, const andi_esa *E, const size_t *que
 	}
 	SubjectIndex S = subject_index(E);
 	S.self = 0xffffffffu;				   // dist_anchor itself has no notion of "self"
+	S.qspec_delta = ctx->pool_spec - ctx->pool_code;
 	if (threshold < (size_t)S.K) S.K = 0;  // the directory assumes K <= threshold
 	WalkPlan plan = plan_walk(ctx, qlens);
 	u32 *d_ids = nullptr, *d_out = nullptr, *d_rec = nullptr;
@@ -156,6 +176,8 @@ extern "C" int andi_dist_anchor(andi_ctx *ctx, const andi_esa *E, const char *qu
 	if (rc) return rc;
 	SubjectIndex S = subject_index(E);
 	S.self = 0xffffffffu;
+	S.qspec_delta = T.spec - T.code;
+	S.qcode_base = T.code, S.qsep3_base = T.sep3;
 	if (threshold < (size_t)S.K) S.K = 0;
 	WalkPlan plan = plan_walk(ctx, std::vector<size_t>{qlen});
 	u32 *d_out = nullptr, *d_rec = nullptr;
@@ -208,6 +230,7 @@ static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_
 		}
 		if (!rc) {
 			SubjectIndex S = subject_index(&E);
+			S.qspec_delta = ctx->pool_spec - ctx->pool_code;
 			rc = launch_walk(ctx, S, ctx->d_queries, nullptr, (u32)n, plan, E.threshold, model,
 							 ctx->any_sep || E.has_sep, true, d_rec, d_out + (i - s_begin) * n * 17);
 		}

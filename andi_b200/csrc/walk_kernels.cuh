@@ -40,6 +40,13 @@ struct SubjectIndex {
 	// prefix-composition table (same word geometry), so comp = qcomp_base + (code - qcode_base)
 	const u64 *qcode_base;
 	const uint4 *qcomp_base;
+	// every query's spec plane lies at the same word distance from its code plane (pool planes and
+	// temporary query planes are each one allocation pair): spec = code + qspec_delta
+	long long qspec_delta;
+	// SPEC fast path: sep3[j] != 0 iff spec words j, j+1 or j+2 hold a separator (k_sep3); the
+	// query's table has the geometry of its code plane: q_sep3 = qsep3_base + (code - qcode_base)
+	const unsigned char *s_sep3;
+	const unsigned char *qsep3_base;
 };
 
 struct QueryView {
@@ -212,14 +219,27 @@ __device__ __forceinline__ void count_anchor(Acc &M, const TextView &q, u32 pq, 
 	M.add(0, a), M.add(5, c), M.add(10, g), M.add(15, t);
 }
 
+// ---- separator hints for the SPEC fast path: out[j] = spec words j, j+1, j+2 hold a separator.
+// A 64-base window starting in word j touches exactly these words, so one byte load decides
+// whether the spec planes have to be read at all. (On concatenated planes a hint may look into
+// the next sequence: a false positive only costs the spec loads.)
+__global__ void k_sep3(const u64 *__restrict__ spec, size_t nwords, unsigned char *__restrict__ out) {
+	size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= nwords) return;
+	u64 x = spec[j];
+	if (j + 1 < nwords) x |= spec[j + 1];
+	if (j + 2 < nwords) x |= spec[j + 2];
+	out[j] = x != 0;
+}
+
 // ---- prefix composition of the pool (LOGDET / ANI fast path): entry j of a sequence holds the
 // number of A, C, G, T among its first 32*j bases, so the composition of any slice
 // (src/model.c:259-278 counts an anchor by its characters) is two entries plus two partial
-// words. One block per sequence, tiles of blockDim words with a running carry. Only valid for
-// sequences without separators (the fast kernels are not used otherwise).
+// words. One block per sequence, tiles of blockDim words with a running carry. Separators
+// are not counted.
 __global__ void __launch_bounds__(256) k_comp_prefix(const QueryView *__restrict__ queries,
 													 const u64 *__restrict__ pool_code, uint4 *__restrict__ pool_comp) {
-	const u64 *code = queries[blockIdx.x].t.code;
+	const u64 *code = queries[blockIdx.x].t.code, *spec = queries[blockIdx.x].t.spec;
 	const u32 len = queries[blockIdx.x].t.len, entries = (len >> 5) + 1;
 	uint4 *out = pool_comp + (code - pool_code);
 	__shared__ uint4 warp_sum[8];
@@ -231,9 +251,10 @@ __global__ void __launch_bounds__(256) k_comp_prefix(const QueryView *__restrict
 		if (j < entries) {
 			u32 nb = min(32u, len - 32u * j);
 			u64 valid = nb == 32u ? ANDI_EVEN_BITS : (ANDI_EVEN_BITS & ((1ULL << (2u * nb)) - 1ULL));
+			valid &= ~spec[j];	// separators are not counted
 			u64 w = code[j], lo = w & valid, hi = (w >> 1) & valid;
 			v.y = (u32)__popcll(lo & ~hi), v.z = (u32)__popcll(hi & ~lo), v.w = (u32)__popcll(hi & lo);
-			v.x = nb - v.y - v.z - v.w;
+			v.x = (u32)__popcll(valid) - v.y - v.z - v.w;
 		}
 		uint4 inc = v;
 #pragma unroll

@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--genomes", type=int, default=0, help="override the number of genomes (experiments only)")
     ap.add_argument("--length", type=int, default=0, help="override the genome length (experiments only)")
+    ap.add_argument("--contigs", type=int, default=0,
+                    help="join-mode shape: every genome is this many contigs joined by '!' (experiments only)")
     ap.add_argument("--rows", type=int, default=0, help="subjects per step and rank (default: one full walk batch)")
     ap.add_argument("--model", default="")
     ap.add_argument("--no-e2e", action="store_true")
@@ -79,7 +81,7 @@ def divergences(g, lo, hi, seed):
 
 # ----------------------------------------------------------------------------- synthetic pool
 
-def make_pool_device(g, ln, lo, hi, seed, device):
+def make_pool_device(g, ln, lo, hi, seed, device, contigs=0):
     """Star phylogeny on the device (shape of test/test_fasta.cxx): uniform base genome, genome k
     gets exactly round(len * d_k) substitutions at distinct uniform positions."""
     import torch
@@ -99,6 +101,9 @@ def make_pool_device(g, ln, lo, hi, seed, device):
             shift = torch.randint(1, 4, (nmut,), dtype=torch.uint8, device=device, generator=gen)
             codes[pos] = (codes[pos] + shift) & 3
         chars[k * stride : k * stride + ln] = lut[codes.long()]
+        if contigs > 1:  # '!' between contigs, as join mode writes them (src/io.c / sequence.c)
+            cut = torch.randint(1, ln - 1, (contigs - 1,), device=device, generator=gen)
+            chars[k * stride + cut] = ord("!")
     offsets = [k * stride for k in range(g)]
     return chars, offsets, [ln] * g, d
 
@@ -246,7 +251,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     g, ln, lo, hi, seed, model = workload_of(args)
-    chars, offsets, lens, d = make_pool_device(g, ln, lo, hi, seed, device)
+    chars, offsets, lens, d = make_pool_device(g, ln, lo, hi, seed, device, args.contigs)
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
@@ -351,7 +356,7 @@ def main():
     achieved = pairs_per_launch * bytes_per_pair / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0
     traffic = None
     tf = ROOT / "profiles" / "walk_traffic.json"
-    if tf.exists() and args.workload == "c4" and not args.genomes and not args.length:
+    if tf.exists() and args.workload == "c4" and not args.genomes and not args.length and not args.contigs:
         t_ = json.loads(tf.read_text())  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
         traffic = (t_["dram_bytes_read"] + t_["dram_bytes_write"]) * (pairs_per_launch / t_["pairs_per_launch"])
     roofline = {

@@ -201,6 +201,52 @@ def test_very_large_genome_properties(ctx):
     assert sub[:16].sum() == n and sub[:16].sum() - sub[[0, 5, 10, 15]].sum() == 500
 
 
+def test_many_contigs(ctx):
+    """Join mode with hundreds of contigs: thousands of suffixes start with (or run into) a
+    separator and share a padded bucket key; they are ordered through the padded-suffix list
+    (sa_bucket.cuh). Includes adjacent separators and duplicated contigs (equal 21-character
+    order keys, settled by direct comparison). Arrays and rows against the oracle."""
+    rng = np.random.default_rng(77)
+    codes = synth.base_genome(60_000, 5)
+    base = synth.ACGT[codes].tobytes()
+    a = bytearray(synth.join_contigs(base, 400, seed=9))
+    for k in rng.choice(len(a) - 2, size=20, replace=False):  # a few adjacent separators
+        a[k] = a[k + 1] = ord("!")
+    contig = synth.ACGT[synth.base_genome(3000, 6)].tobytes()
+    other = synth.ACGT[synth.base_genome(20_000, 7)].tobytes()
+    b = b"!".join([contig, other[:7000], contig, contig, other[7000:], contig[:1500]])
+    c = synth.join_contigs(synth.ACGT[synth.mutate(codes, 0.02, seed=3)].tobytes(), 250, seed=10)
+    seqs = [bytes(a), b, c, base]
+    ctx.set_pool(seqs)
+    for k, s in enumerate(seqs[:3]):
+        o = oracle.OracleEsa(s)
+        e = ctx.esa_build(k)
+        got = e.download()
+        assert np.array_equal(got["SA"], o.array("SA")), ("SA", k)
+        assert np.array_equal(got["LCP"], o.array("LCP")), ("LCP", k)
+        e.free(), o.close()
+    for model in ("JC", "LOGDET"):
+        assert np.array_equal(ctx.dist_rows(model=model), oracle.rows(seqs, model)), model
+
+
+def test_large_joined_genomes_against_reference(ctx):
+    """5 Mbp draft-assembly shape (N = 10 M > 8 M: radix bucketing path) with 300 contigs each,
+    against the reference itself: suffix array, LCP and the rows."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    plain = synth.star_phylogeny(2, 5_000_000, [0.0, 0.02], seed=515)
+    seqs = [synth.join_contigs(plain[0], 300, seed=1), synth.join_contigs(plain[1], 300, seed=2)]
+    ctx.set_pool(seqs)
+    h = oracle.RefEsaHandle(seqs[0])
+    e = ctx.esa_build(0)
+    got = e.download()
+    assert np.array_equal(got["SA"], h.array("SA"))
+    assert np.array_equal(got["LCP"], h.array("LCP"))
+    e.free()
+    want, _ = oracle.ref_rows(seqs, "JC", threads=2)
+    assert np.array_equal(ctx.dist_rows(), want)
+
+
 def test_pathological_repeats(ctx):
     """Low-complexity and tandem-repeat texts: every suffix ties for thousands of characters, so
     the bucket sorter hands everything to the doubling rounds and the direct LCP overflows into
