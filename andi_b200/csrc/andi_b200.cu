@@ -77,6 +77,7 @@ struct andi_esa {
 	u64 *dir = nullptr;
 	PresenceLevels present{};
 	unsigned char *plen = nullptr;
+	u64 *fdir = nullptr;  // 4^K: the walk's own view of the directory (k_fast_dir)
 	int K = 0;
 	bool has_sep = false;
 	bool full = false;
@@ -101,7 +102,7 @@ static thread_local std::string g_create_err;
 	} while (0)
 
 static inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
-static inline size_t plane_words(size_t chars) { return chars / 32 + 3; }  // >= 2 guard words
+static inline size_t plane_words(size_t chars) { return chars / 32 + 4; }  // >= 3 guard words (window64)
 
 template <class T>
 static cudaError_t dalloc(andi_ctx *ctx, T **p, size_t count) {
@@ -534,7 +535,7 @@ extern "C" int andi_esa_download(const andi_esa *E, int32_t *SA, int32_t *LCP, i
 static SubjectIndex subject_index(const andi_esa *E) {
 	SubjectIndex S;
 	S.rs = rs_view(E);
-	S.SA = E->SA, S.LCP = E->LCP, S.dir = E->dir, S.plen = E->plen;
+	S.SA = E->SA, S.LCP = E->LCP, S.dir = E->dir, S.plen = E->plen, S.fdir = E->fdir;
 	S.K = E->K, S.threshold = E->threshold, S.self = E->self, S.has_sep = E->has_sep;
 	S.qcode_base = nullptr, S.qcomp_base = nullptr, S.qspec_delta = 0;
 	S.s_sep3 = E->sep3, S.qsep3_base = nullptr;
@@ -556,7 +557,7 @@ __global__ void k_pack_many(const unsigned char *__restrict__ chars, const size_
 	u32 k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= nq) return;
 	const unsigned char *src = chars + coff[k];
-	u32 n = lens[k], nw = n / 32 + 3, sep = 0;
+	u32 n = lens[k], nw = n / 32 + 4, sep = 0;  // = plane_words(n)
 	for (u32 w = 0; w < nw; w++) {
 		u64 cw = 0, sw = 0;
 		for (u32 d = 0; d < 32 && w * 32 + d < n; d++) {

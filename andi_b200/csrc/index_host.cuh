@@ -215,7 +215,7 @@ static int build_full(andi_ctx *ctx, andi_esa *E) {
 static void esa_release(andi_esa *E) {
 	andi_ctx *ctx = E->ctx;
 	dfree(ctx, E->code), dfree(ctx, E->spec), dfree(ctx, E->sep3), dfree(ctx, E->SA), dfree(ctx, E->LCP);
-	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->plen), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
+	dfree(ctx, E->dir), dfree(ctx, E->present.bits), dfree(ctx, E->plen), dfree(ctx, E->fdir), dfree(ctx, E->CLD), dfree(ctx, E->FVC);
 	dfree(ctx, E->cache);
 	E->cap_words = E->cap_n = E->cap_kmers = E->cap_present = 0;
 	E->full = false;
@@ -240,9 +240,10 @@ static int esa_ensure(andi_ctx *ctx, andi_esa *E) {
 	if (E->K >= 2) {
 		const size_t kmers = (size_t)1 << (2 * E->K);
 		if (kmers > E->cap_kmers) {
-			dfree(ctx, E->dir), dfree(ctx, E->plen);
+			dfree(ctx, E->dir), dfree(ctx, E->plen), dfree(ctx, E->fdir);
 			CK(dalloc(ctx, &E->dir, kmers));
 			CK(dalloc(ctx, &E->plen, kmers));
+			CK(dalloc(ctx, &E->fdir, kmers));
 			E->cap_kmers = kmers;
 		}
 		size_t words = 0;
@@ -439,6 +440,10 @@ rebuild:
 		}
 	}
 	if (!rc && h_flags[1]) rc = build_lcp_phi(ctx, E);
+	if (!rc) {	// suffix array and prefix lengths are final: the walk's view of the directory
+		k_fast_dir<<<nblocks(kmers, 256), 256, 0, st>>>(E->dir, E->SA, E->plen, E->fdir, (u32)kmers);
+		ctx->st.esa_launches++;
+	}
 	return rc;
 }
 

@@ -137,7 +137,7 @@ k_pack_tails(const unsigned char *__restrict__ chars, const PackSeq *__restrict_
 	const u32 k = blockIdx.x;
 	const PackSeq s = seqs[k];
 	const u32 first_word = full_tiles[k] * (ANDI_PACK_TILE / 32u);
-	const u32 nwords = s.len / 32u + 3u;
+	const u32 nwords = s.len / 32u + 4u;  // = plane_words(len)
 	u32 gc = 0, sep = 0;
 	for (u32 w = first_word + threadIdx.x; w < nwords; w += blockDim.x) {
 		u64 cw = 0, sw = 0;

@@ -294,6 +294,30 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 	dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
 }
 
+// The walk's view of the directory, one 8-byte entry per k-mer so that the common lookups cost
+// ONE table access (the tables compete with the streaming queries for L2):
+//   tag 0 (absent k-mer)    low bits = plen: the longest prefix of the k-mer present in RS, which
+//                           is all the walk needs (no anchor can result below K)
+//   tag 1 (one suffix)      low 32 bits = its text position: the compare starts without the
+//                           dependent suffix-array load
+//   tag 2 (several)         low 32 bits = first SA index, bits 32..61 = their number
+#define ANDI_FDIR_TAG(e) ((u32)((e) >> 62))
+__global__ void k_fast_dir(const u64 *__restrict__ dir64, const u32 *__restrict__ SA,
+						   const unsigned char *__restrict__ plen, u64 *__restrict__ fdir, u32 kmers) {
+	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
+	if (key >= kmers) return;
+	u64 de = dir64[key];
+	u32 first = (u32)de, count = (u32)(de >> 32);
+	u64 out;
+	if (count == 0)
+		out = plen[key];
+	else if (count == 1)
+		out = (1ULL << 62) | SA[first];
+	else
+		out = (2ULL << 62) | ((u64)count << 32) | first;
+	fdir[key] = out;
+}
+
 // Only when k_bucket_sort reported ties: group heads, ranks and "ambiguous" flags of every
 // suffix, the input of the doubling rounds (index_host.cuh). Buckets are laid out as
 // k_bucket_sort left them.

@@ -8,8 +8,9 @@
 // Byte equality of the reference (`S[a] == Q[b]`, src/process.c:59-65, src/esa.c:408,546,592)
 // is therefore "code pair equal and spec pair equal", and the byte order the suffix array
 // is built under ('\0' < '!' < '#' < ';' < A < C < G < T) is sym3() below.
-// Every plane is allocated with two zero guard words so a 32-character window may start at
-// any position up to and including the text length.
+// Every plane is 16-byte aligned and allocated with zero guard words (plane_words()) so a
+// 32-character window may start at any position up to and including the text length and a
+// 64-character window (two aligned word pairs) at any position below it.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -40,17 +41,30 @@ __device__ __forceinline__ u64 window32(const u64 *__restrict__ w, u32 pos) {
 	return ((u64)hi << 32) | lo;
 }
 
-// 64 characters starting at pos (three word loads): lo = characters 0..31, hi = 32..63.
-// The caller guarantees pos < text length, so word (pos>>5)+2 is inside the guarded plane.
+// 64 characters starting at pos: lo = characters 0..31, hi = 32..63. The three words i..i+2
+// that hold them are fetched as the two ALIGNED 16-byte pairs that cover them (planes are 16-byte
+// aligned, plane_words() leaves room for the last pair): two 128-bit requests instead of three
+// 64-bit ones -- the walk is bound by L1/TEX request throughput as much as by issue slots.
+// The caller guarantees pos < text length.
 __device__ __forceinline__ void window64(const u64 *__restrict__ w, u32 pos, u64 &lo, u64 &hi) {
 	u32 i = pos >> 5, sh = (pos & 31u) * 2u;
-	u64 a = __ldg(w + i), b = __ldg(w + i + 1), c = __ldg(w + i + 2);
-	u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), c0 = (u32)c, c1 = (u32)(c >> 32);
-	bool upper = sh >= 32u;
-	u32 x0 = upper ? a1 : a0, x1 = upper ? b0 : a1, x2 = upper ? b1 : b0, x3 = upper ? c0 : b1, x4 = upper ? c1 : c0;
+	const uint4 *pair = reinterpret_cast<const uint4 *>(w) + (i >> 1);
+	uint4 a = __ldg(pair), b = __ldg(pair + 1);
+	// eight 32-bit pieces a.x a.y a.z a.w b.x b.y b.z b.w; the window starts at piece 2*(i&1) + (sh>=32)
+	bool odd = i & 1u, upper = sh >= 32u;
+	u32 y0 = odd ? a.z : a.x, y1 = odd ? a.w : a.y, y2 = odd ? b.x : a.z, y3 = odd ? b.y : a.w, y4 = odd ? b.z : b.x,
+		y5 = odd ? b.w : b.y;
+	u32 x0 = upper ? y1 : y0, x1 = upper ? y2 : y1, x2 = upper ? y3 : y2, x3 = upper ? y4 : y3, x4 = upper ? y5 : y4;
 	u32 s = sh & 31u;
 	lo = ((u64)__funnelshift_r(x1, x2, s) << 32) | __funnelshift_r(x0, x1, s);
 	hi = ((u64)__funnelshift_r(x3, x4, s) << 32) | __funnelshift_r(x2, x3, s);
+}
+
+// 16 characters starting at pos, from the 32-bit halves of the plane (little endian: the low
+// half of a word holds its characters 0..15). pos < text length.
+__device__ __forceinline__ u32 window16(const u64 *__restrict__ w, u32 pos) {
+	const u32 *h = reinterpret_cast<const u32 *>(w) + (pos >> 4);
+	return __funnelshift_r(__ldg(h), __ldg(h + 1), (pos & 15u) * 2u);
 }
 
 __device__ __forceinline__ u32 code_at(const u64 *__restrict__ w, u32 pos) {

@@ -27,7 +27,7 @@
 //   DIR     k-mer directory + prefix-length probe      CAND   fetch SA[candidate]
 //   SLOW    anything unusual -> longest_match<false>() of walk_kernels.cuh
 //   DECIDE  process.c:160-196: pairing, accounting, advance
-//   COLS    classify up to 32 gap columns (model.c:309-337)
+//   COLS    classify up to 16 gap columns (model.c:309-337)
 //
 // The single-column gap -- by far the most common one, a lone substitution between two
 // anchors -- costs no memory op at all: the class of the column that ended a compare is
@@ -44,7 +44,7 @@ struct LaneCompare {
 };
 
 struct LaneLookup {
-	u32 key, cand, hi, best, best_p, best_cnt, best_mm, short_len;
+	u32 key, cand, hi, best, best_p, best_cnt, best_mm;
 };
 
 struct LaneResult {
@@ -121,9 +121,9 @@ __device__ __forceinline__ void cmp_window(u32 &op, LaneCompare &C, LaneLookup &
 			R.s = L.best_p, R.len = L.best, R.mm = L.best_mm;
 			op = OP_DECIDE;
 		} else {
-			// only suffixes with a separator in their first K characters were in the range
-			R.found = 0, R.len = L.short_len, R.s = 0, R.mm = 0;
-			op = OP_DECIDE;
+			// cannot happen (the directory counts only suffixes that carry the whole k-mer):
+			// leave it to the generic search
+			op = OP_SLOW;
 		}
 	}
 }
@@ -155,7 +155,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 	u32 b_pos = 0, b_ls = 0, b_lq = 0, b_ll = 0, b_pm = 0;
 	u32 set = 0, sign = 1;
 	LaneCompare C = {0, 0, 0, 0};
-	LaneLookup L = {0, 0, 0, 0, 0, 0, 0, 0};
+	LaneLookup L = {0, 0, 0, 0, 0, 0, 0};
 	LaneResult R = {0, 0, 0, 0};
 	u32 cols_s = 0, cols_q = 0, cols_left = 0;
 
@@ -260,19 +260,26 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ DIR
 		if (op == OP_DIR) {
-			u64 de = __ldg(S.dir + L.key);
-			u32 t0 = (u32)de, t1 = t0 + (u32)(de >> 32);
-			L.short_len = __ldg(S.plen + L.key);  // the answer if the k-mer turns out to be absent
-			if (t1 > t0) {
-				if (t1 - t0 <= ANDI_SCAN_MAX) {
-					L.cand = t0, L.hi = t1, L.best = 0, L.best_cnt = 0, L.best_p = 0, L.best_mm = 0;
+			u64 fe = __ldg(S.fdir + L.key);
+			u32 tag = ANDI_FDIR_TAG(fe);
+			L.best = 0, L.best_cnt = 0, L.best_p = 0, L.best_mm = 0;
+			if (tag == 0u) {  // absent k-mer: only the length of the match matters
+				R.found = 0, R.len = (u32)fe, R.s = 0, R.mm = 0;
+				op = OP_DECIDE;
+			} else if (tag == 1u) {	 // one suffix starts with this k-mer: compare it right away
+				u32 p = (u32)fe, rem = qlen - a_pos;
+				u32 run = SPEC ? N - p : (p < mid ? mid - p : (p == mid ? 0u : N - p));
+				L.cand = 0, L.hi = 1;
+				C.cs = p, C.ck = 0, C.clim = min(rem, run), C.is_cand = 1;
+				op = OP_CMP;
+			} else {
+				u32 t0 = (u32)fe, cnt = (u32)(fe >> 32) & 0x3fffffffu;
+				if (cnt <= ANDI_SCAN_MAX) {
+					L.cand = t0, L.hi = t0 + cnt;
 					op = OP_CAND;
 				} else {
 					op = OP_SLOW;
 				}
-			} else {
-				R.found = 0, R.len = L.short_len, R.s = 0, R.mm = 0;
-				op = OP_DECIDE;
 			}
 		}
 
@@ -362,24 +369,26 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 		__syncwarp();  // phase boundary: every lane of the warp re-converges here
 		// ------------------------------------------------------------ COLS: model.c:309-337
 		if (op == OP_COLS) {
-			u32 span = min(32u, cols_left);
-			u64 qw = window32(q_code, cols_q), sw = window32(s_code, cols_s);
-			u64 valid = span == 32u ? ANDI_EVEN_BITS : (ANDI_EVEN_BITS & ((1ULL << (2u * span)) - 1ULL));
-			if (cols_s <= mid && mid - cols_s < span) valid &= ~(1ULL << (2u * (mid - cols_s)));  // '#' column
+			// 16 columns per pass in 32-bit arithmetic: a gap behind a lucky anchor is at most
+			// `threshold` columns wide, and half-width masks / popcounts halve the phase
+			u32 span = min(16u, cols_left);
+			u32 qw = window16(q_code, cols_q), sw = window16(s_code, cols_s);
+			u32 valid = span == 16u ? 0x55555555u : (0x55555555u & ((1u << (2u * span)) - 1u));
+			if (cols_s <= mid && mid - cols_s < span) valid &= ~(1u << (2u * (mid - cols_s)));	// '#' column
 			if (SPEC && (__ldg(S.s_sep3 + (cols_s >> 5)) | __ldg(S.qsep3_base + (q_code - S.qcode_base) + (cols_q >> 5))))
-				valid &= ~(window32(s_spec, cols_s) | window32(q_code + S.qspec_delta, cols_q));
-			u64 x = qw ^ sw;
-			u64 neq = (x | (x >> 1)) & valid, eq = valid & ~neq;
-			u64 lo = qw & ANDI_EVEN_BITS, hb = (qw >> 1) & ANDI_EVEN_BITS;
+				valid &= ~(window16(s_spec, cols_s) | window16(q_code + S.qspec_delta, cols_q));
+			u32 x = qw ^ sw;
+			u32 neq = (x | (x >> 1)) & valid, eq = valid & ~neq;
+			u32 lo = qw & 0x55555555u, hb = (qw >> 1) & 0x55555555u;
 			u32 *col = &cells[set][0][tid];
-			col[0 * ANDI_WALK_THREADS] += (u32)__popcll(eq & ~hb & ~lo) * sign;
-			col[5 * ANDI_WALK_THREADS] += (u32)__popcll(eq & ~hb & lo) * sign;
-			col[10 * ANDI_WALK_THREADS] += (u32)__popcll(eq & hb & ~lo) * sign;
-			col[15 * ANDI_WALK_THREADS] += (u32)__popcll(eq & hb & lo) * sign;
+			col[0 * ANDI_WALK_THREADS] += (u32)__popc(eq & ~hb & ~lo) * sign;
+			col[5 * ANDI_WALK_THREADS] += (u32)__popc(eq & ~hb & lo) * sign;
+			col[10 * ANDI_WALK_THREADS] += (u32)__popc(eq & hb & ~lo) * sign;
+			col[15 * ANDI_WALK_THREADS] += (u32)__popc(eq & hb & lo) * sign;
 			while (neq) {
-				u32 d2 = (u32)(__ffsll((long long)neq) - 1);
+				u32 d2 = (u32)(__ffs((int)neq) - 1);
 				neq &= neq - 1;
-				u32 cls = ((((u32)(sw >> d2)) & 3u) << 2) | (((u32)(qw >> d2)) & 3u);
+				u32 cls = (((sw >> d2) & 3u) << 2) | ((qw >> d2) & 3u);
 				col[cls * ANDI_WALK_THREADS] += sign;
 			}
 			cols_s += span, cols_q += span, cols_left -= span;
