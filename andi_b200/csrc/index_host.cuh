@@ -396,10 +396,10 @@ rebuild:
 	if (sep) {
 		rc = padded_finish(ctx, E, rs);
 		if (rc) return rc;
-		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags);
+		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, N <= ANDI_BUCKET_ATOMIC_MAX);
 		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	} else {
-		k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, E->dir, b.flags);
+		k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, E->dir, b.flags, N <= ANDI_BUCKET_ATOMIC_MAX);
 		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	}
 	ctx->st.esa_launches += 2;

@@ -221,19 +221,22 @@ __global__ void k_padded_place(int K, const u64 *__restrict__ key, const u32 *__
 }
 
 // dir64[key] = first SA index of the suffixes that really start with this k-mer (no
-// separator inside) | their number << 32. *n_ambiguous counts the suffixes that are still tied
+// separator inside) | their number << 32; first + number = end of the bucket. *n_ambiguous counts the suffixes that are still tied
 // with a neighbour; their groups are materialised by k_bucket_groups only when there are any.
 template <bool SPEC>
 __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
 							  const u32 *__restrict__ fvalid, u32 *__restrict__ SA, u64 *__restrict__ dir64,
-							  u32 *__restrict__ n_ambiguous) {
+							  u32 *__restrict__ n_ambiguous, u32 empty_known) {
 	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
 	if (key >= (1u << (2 * K))) return;
 	const u32 e = bend[key];
 	// fvalid given: the padded suffixes already stand sorted in [bstart, fvalid) (k_padded_place)
 	const u32 b = fvalid ? min(fvalid[key], e) : bstart[key], s = e - b;
 	if (e == bstart[key]) {
-		dir64[key] = 0;
+		// first + count is the END of the bucket for every key, so the start of bucket k is the
+		// end of k-1 (the generic search narrows its range with that). The radix bucketing path
+		// does not know where an empty bucket lies: 0xffffffff = unknown.
+		dir64[key] = empty_known ? (u64)e : 0xffffffffULL;
 		return;
 	}
 	if (fvalid && s > ANDI_SORT_MAX) {	// valid suffixes only: one group of depth K for the doubling rounds

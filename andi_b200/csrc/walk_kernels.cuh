@@ -63,11 +63,12 @@ struct MatchResult {
 };
 
 // ---- generic search: binary search of the query among the suffixes SA[lo, hi) in the
-// reference's byte order, then the better neighbour; uniqueness from the LCP array.
+// reference's byte order, then the better neighbour (looked for inside [nlo, nhi));
+// uniqueness from the LCP array.
 template <bool SPEC>
 __device__ MatchResult search_range(const SubjectIndex &S, const TextView &q, u32 qpos, u32 rem,
-									u32 lo, u32 hi) {
-	const u32 lo0 = lo, hi0 = hi;
+									u32 lo, u32 hi, u32 nlo, u32 nhi) {
+	const u32 lo0 = nlo, hi0 = nhi;
 	while (lo < hi) {
 		u32 mid = lo + ((hi - lo) >> 1);
 		u32 p = S.SA[mid];
@@ -124,7 +125,33 @@ __device__ __forceinline__ MatchResult longest_match(const SubjectIndex &S, cons
 			if (sw & ((1ULL << (2 * K)) - 1ULL)) direct = false;
 		}
 	}
-	if (!direct) return search_range<SPEC>(S, q, qpos, rem, 0, S.rs.len);
+	if (!direct) {
+		// A separator among the first K query characters, or a query tail shorter than K. The
+		// padded bucket key (sa_bucket.cuh) is monotone in suffix order, so the query's place
+		// among the suffixes lies inside the bucket of ITS padded key: [end of bucket key-1,
+		// end of bucket key]. The binary search starts from that range instead of [0, N).
+		u32 lo = 0, hi = S.rs.len;
+		if (K > 0 && rem > 0) {
+			u32 r = min(rem, (u32)K);
+			u64 w = window32(q.code, qpos);
+			if (SPEC) {
+				u64 sw = window32(q.spec, qpos);
+				if (sw) r = min(r, (u32)(__ffsll((long long)sw) - 1) >> 1);
+			}
+			w &= (1ULL << (2u * r)) - 1ULL;
+			u32 key = kmer_key(w, K);
+			u64 de = __ldg(S.dir + key);
+			bool known = (u32)de != 0xffffffffu;
+			u32 end = (u32)de + (u32)(de >> 32), start = 0;
+			if (key) {
+				u64 dp = __ldg(S.dir + key - 1);
+				known = known && (u32)dp != 0xffffffffu;
+				start = (u32)dp + (u32)(dp >> 32);
+			}
+			if (known && start <= end && end <= S.rs.len) lo = start, hi = end;
+		}
+		return search_range<SPEC>(S, q, qpos, rem, lo, hi, 0, S.rs.len);
+	}
 
 	u32 key = kmer_key(cw, K);
 	u64 de = __ldg(S.dir + key);
@@ -143,7 +170,7 @@ __device__ __forceinline__ MatchResult longest_match(const SubjectIndex &S, cons
 			}
 			r.len = best, r.at = at, r.unique = cnt == 1, r.found_pos = true;
 		} else {
-			r = search_range<SPEC>(S, q, qpos, rem, lo, hi);
+			r = search_range<SPEC>(S, q, qpos, rem, lo, hi, lo, hi);
 		}
 		if (r.len >= (u32)K) return r;
 	}
@@ -554,7 +581,7 @@ __global__ void k_get_match(SubjectIndex S, const QueryView *__restrict__ querie
 	if (k >= nq) return;
 	const TextView &q = queries[k].t;
 	MatchResult m = longest_match<SPEC>(S, q, 0, q.len);
-	MatchResult g = search_range<SPEC>(S, q, 0, q.len, 0, S.rs.len);
+	MatchResult g = search_range<SPEC>(S, q, 0, q.len, 0, S.rs.len, 0, S.rs.len);
 	Inter r;
 	r.m = -1;
 	if (m.len != g.len || (m.found_pos && m.unique != g.unique)) {
