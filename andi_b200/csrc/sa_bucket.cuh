@@ -273,6 +273,24 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 		dir64[key] = (u64)front | ((u64)valid << 32);
 		return;
 	}
+	if (s <= 2) {
+		// nine buckets in ten: one suffix (nothing to order) or two (one comparison decides order
+		// and tie) -- kept out of the local-memory array of the general case
+		if (s == 0) {  // only padded suffixes (already placed)
+			dir64[key] = (u64)e;
+			return;
+		}
+		u32 p0 = SA[b], p1 = s == 2 ? SA[b + 1] : 0u;
+		valid = fvalid ? s : (u32)!is_padded<SPEC>(rs, p0, K);
+		if (s == 2) {
+			if (!fvalid) valid += (u32)!is_padded<SPEC>(rs, p1, K);
+			int c = compare_suffixes<SPEC>(rs, p0, p1, ANDI_SORT_CAP);
+			if (c > 0) SA[b] = p1, SA[b + 1] = p0;
+			if (c == 0) atomicAdd(n_ambiguous, 2u);
+		}
+		dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
+		return;
+	}
 	u32 v[ANDI_SORT_MAX];
 #pragma unroll
 	for (int x = 0; x < ANDI_SORT_MAX; x++) v[x] = x < (int)s ? SA[b + x] : 0u;
