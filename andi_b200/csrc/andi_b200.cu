@@ -397,10 +397,17 @@ static TextView rs_view(const andi_esa *E) {
 	return t;
 }
 
-static int choose_depth(u32 N, u32 threshold) {
-	// directory depth ~ log4(N): about one suffix per bucket; never deeper than the anchor
+static int choose_depth(u32 N, u32 threshold, unsigned long long query_bases = 0) {
+	// Directory depth ~ log4(N): about one suffix per bucket; never deeper than the anchor
 	// threshold (below it only the match LENGTH matters, see longest_match) nor than 14.
+	// One level deeper (a quarter of a suffix per bucket: most lookups end at the directory
+	// entry or at its only suffix, and whole warps skip the candidate phase) makes the walk 12 %
+	// faster but every table pass of the build four times longer; that pays once a subject is
+	// walked by about a gigabase of queries (measured on 3085 x 2.1 Mbp: K 11 -> 12 moves the walk
+	// 7.43 -> 6.55 ms and the build 0.46 -> 0.74 ms per subject; K 13: 6.30 and 2.2 ms).
 	int k = (int)floor(log((double)N) / log(4.0) + 0.5);
+	if (query_bases >= 1000000000ULL) k += 1;
+	if (const char *bias = getenv("ANDI_B200_DEPTH_BIAS")) k += atoi(bias);	 // experiments only
 	k = std::max(k, 4);
 	k = std::min(k, 14);
 	if (threshold < (u32)k) k = (int)threshold;

@@ -203,6 +203,8 @@ static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_
 	CK(cudaSetDevice(ctx->device));
 	const size_t n = ctx->n, rows = s_end - s_begin;
 	WalkPlan plan = plan_walk(ctx, ctx->len);
+	unsigned long long total_bases = 0;
+	for (size_t l : ctx->len) total_bases += l;
 	u32 *d_rec = nullptr, *d_out = nullptr;
 	CK(dalloc(ctx, &d_rec, plan.record_words));
 	if (out_on_device)
@@ -218,7 +220,7 @@ static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_
 		E.has_sep = ctx->has_sep[i] != 0;
 		E.self = (u32)i;
 		E.threshold = (u32)andi_threshold(p_value, ctx->gc[i], E.N);
-		E.K = choose_depth(E.N, E.threshold);
+		E.K = choose_depth(E.N, E.threshold, total_bases);
 		size_t nw = plane_words(E.N);
 		rc = esa_ensure(ctx, &E);
 		if (!rc) {

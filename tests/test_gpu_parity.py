@@ -169,6 +169,17 @@ def test_chunk_boundaries_are_exact(ctx, chunk, monkeypatch):
             assert np.array_equal(got, want), (name, model, chunk)
 
 
+@pytest.mark.parametrize("bias", [-2, 1, 2])
+def test_directory_depth_does_not_change_results(ctx, bias, monkeypatch):
+    """The k-mer directory depth K is a tuning choice (one level deeper for large pools,
+    choose_depth in andi_b200.cu): shallower and deeper directories must give the same rows."""
+    monkeypatch.setenv("ANDI_B200_DEPTH_BIAS", str(bias))
+    for name, seqs in stress_sequences().items():
+        ctx.set_pool(seqs)
+        for model in ("JC", "ANI"):
+            assert np.array_equal(ctx.dist_rows(model=model), oracle.rows(seqs, model)), (name, model, bias)
+
+
 def test_large_genomes_against_reference(ctx):
     """20 Mbp genomes (N = 40 M): 32-bit index arithmetic, directory depth 13, several chunks
     per thread. Checked against the reference itself (oracle/_ref) because the oracle's
