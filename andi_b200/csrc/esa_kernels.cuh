@@ -220,22 +220,9 @@ __global__ void k_lcp_from_plcp(const u32 *__restrict__ SA, const int32_t *__res
 // << 32; they are contiguous in SA.
 //
 // Presence bitmaps: level m (1 <= m < K) has bit x set iff the m-mer x occurs in RS. Level K-1
-// comes from the directory counts, lower levels by OR-ing groups of four bits, and suffixes
+// is left by k_bucket_sort (a folded warp ballot of its counts), lower levels come by OR-ing groups of four bits, and suffixes
 // that hit a separator / the end before K characters are patched in. They only serve to
 // build the prefix-length table (k_prefix_len) and are freed afterwards.
-__global__ void k_presence_from_dir(const u64 *__restrict__ dir, u32 nbits, u32 *__restrict__ bits) {
-	u32 w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w * 32u >= nbits) return;
-	u32 out = 0;
-	for (u32 b = 0; b < 32; b++) {
-		u32 x = w * 32u + b;
-		if (x >= nbits) break;
-		u64 any = (dir[4u * x] | dir[4u * x + 1] | dir[4u * x + 2] | dir[4u * x + 3]) >> 32;
-		if (any) out |= 1u << b;
-	}
-	bits[w] = out;
-}
-
 __global__ void k_presence_down(const u32 *__restrict__ upper, u32 nbits, u32 *__restrict__ lower) {
 	u32 w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w * 32u >= nbits) return;
@@ -273,21 +260,41 @@ __global__ void k_presence_patch(TextView rs, int K, PresenceLevels lv, u32 firs
 	}
 }
 
-// plen[x] for every k-mer x: length of the longest prefix of x (0 .. K-1) that occurs in RS.
-// This is what a lookup of an ABSENT k-mer returns, so the walk needs one byte load instead
-// of probing the bitmap levels.
-__global__ void k_prefix_len(PresenceLevels lv, int K, unsigned char *__restrict__ plen) {
-	u32 x = blockIdx.x * blockDim.x + threadIdx.x;
-	if (x >= (1u << (2 * K))) return;
+// plen[x] for every k-mer x: length of the longest prefix of x (0 .. K-1) that occurs in RS --
+// what a lookup of an ABSENT k-mer returns. It does not depend on the last character, so one
+// thread serves the four k-mers 4y..4y+3 of a (K-1)-mer y: one probe sequence, one 32-byte
+// directory read, and the four entries of the walk's own directory view (fdir, see
+// sa_bucket.cuh: tag 0 + plen / tag 1 + text position of the only suffix / tag 2 + first index
+// and count) in the same pass. Runs once the suffix array is final.
+__global__ void k_prefix_len(PresenceLevels lv, int K, const u64 *__restrict__ dir, const u32 *__restrict__ SA,
+							 unsigned char *__restrict__ plen, u64 *__restrict__ fdir) {
+	u32 y = blockIdx.x * blockDim.x + threadIdx.x;
+	if (y >= (1u << (2 * (K - 1)))) return;
 	u32 l = 0;
 	for (int m = K - 1; m >= 1; m--) {
-		u32 y = x >> (2 * (K - m));
-		if ((lv.bits[lv.offset[m] + (y >> 5)] >> (y & 31u)) & 1u) {
+		u32 z = y >> (2 * (K - 1 - m));
+		if ((lv.bits[lv.offset[m] + (z >> 5)] >> (z & 31u)) & 1u) {
 			l = (u32)m;
 			break;
 		}
 	}
-	plen[x] = (unsigned char)l;
+	reinterpret_cast<u32 *>(plen)[y] = l * 0x01010101u;
+	const ulonglong2 *din = reinterpret_cast<const ulonglong2 *>(dir) + 2 * (size_t)y;
+	ulonglong2 d01 = din[0], d23 = din[1];
+	u64 de[4] = {d01.x, d01.y, d23.x, d23.y}, out[4];
+#pragma unroll
+	for (int c = 0; c < 4; c++) {
+		u32 first = (u32)de[c], count = (u32)(de[c] >> 32);
+		if (count == 0)
+			out[c] = l;
+		else if (count == 1)
+			out[c] = (1ULL << 62) | SA[first];
+		else
+			out[c] = (2ULL << 62) | ((u64)count << 32) | first;
+	}
+	ulonglong2 *dout = reinterpret_cast<ulonglong2 *>(fdir) + 2 * (size_t)y;
+	dout[0] = make_ulonglong2(out[0], out[1]);
+	dout[1] = make_ulonglong2(out[2], out[3]);
 }
 
 // ------------------------------------------------------------------ E3: FVC

@@ -143,21 +143,22 @@ static int build_lcp_phi(andi_ctx *ctx, andi_esa *E) {
 	return ANDI_OK;
 }
 
-// Presence bitmaps (levels 1..K-1) from the directory counts, then the prefix-length table.
-static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
-	cudaStream_t st = ctx->stream;
-	const int K = E->K;
-	const size_t kmers = (size_t)1 << (2 * K);
-	TextView rs = rs_view(E);
+// Word offsets of the presence levels 1..K-1 inside E->present.bits (sized by esa_ensure).
+static void presence_layout(andi_esa *E) {
 	size_t words = 0;
-	for (int m = 1; m < K; m++) {
+	for (int m = 1; m < E->K; m++) {
 		E->present.offset[m] = (u32)words;
 		words += (((size_t)1 << (2 * m)) + 31) / 32;
 	}
-	(void)words;  // E->present.bits was sized by esa_ensure
-	u32 top_bits = 1u << (2 * (K - 1));
-	k_presence_from_dir<<<nblocks((top_bits + 31) / 32, 256), 256, 0, st>>>(E->dir, top_bits,
-																			 E->present.bits + E->present.offset[K - 1]);
+}
+
+// Level K-1 of the presence bitmaps was left by k_bucket_sort; derive the lower levels, patch in
+// the suffixes that end early, then the prefix-length table and the walk's directory view.
+// Needs the final suffix array (the view holds text positions).
+static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
+	cudaStream_t st = ctx->stream;
+	const int K = E->K;
+	TextView rs = rs_view(E);
 	for (int m = K - 2; m >= 1; m--) {
 		u32 nb = 1u << (2 * m);
 		k_presence_down<<<nblocks((nb + 31) / 32, 256), 256, 0, st>>>(E->present.bits + E->present.offset[m + 1], nb,
@@ -171,8 +172,8 @@ static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
 		k_presence_patch<<<1, 32, 0, st>>>(rs, K, E->present, E->n >= k ? E->n - k : 0, k + 1);
 		k_presence_patch<<<1, 32, 0, st>>>(rs, K, E->present, E->N >= k ? E->N - k : 0, k + 1);
 	}
-	k_prefix_len<<<nblocks(kmers, 256), 256, 0, st>>>(E->present, K, E->plen);
-	ctx->st.esa_launches += 3 + (K - 1);
+	k_prefix_len<<<nblocks((size_t)1 << (2 * (K - 1)), 256), 256, 0, st>>>(E->present, K, E->dir, E->SA, E->plen, E->fdir);
+	ctx->st.esa_launches += 3 + (K - 2);
 	return ANDI_OK;
 }
 
@@ -393,17 +394,19 @@ rebuild:
 		ctx->st.esa_launches += 2;
 		ctx->st.cub_calls += 1;
 	}
+	presence_layout(E);
+	u32 *present_top = E->present.bits + E->present.offset[K - 1];
+	CK(cudaMemsetAsync(present_top, 0, ((((size_t)1 << (2 * (K - 1))) + 31) / 32) * sizeof(u32), st));
 	if (sep) {
 		rc = padded_finish(ctx, E, rs);
 		if (rc) return rc;
-		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, N <= ANDI_BUCKET_ATOMIC_MAX);
+		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, N <= ANDI_BUCKET_ATOMIC_MAX, present_top);
 		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	} else {
-		k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, E->dir, b.flags, N <= ANDI_BUCKET_ATOMIC_MAX);
+		k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, E->dir, b.flags, N <= ANDI_BUCKET_ATOMIC_MAX, present_top);
 		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	}
 	ctx->st.esa_launches += 2;
-	rc = build_prefix_lengths(ctx, E);
 	u32 h_flags[4] = {0, 0, 0, 0};
 	if (!rc) {
 		CK(cudaMemcpyAsync(h_flags, b.flags, sizeof h_flags, cudaMemcpyDeviceToHost, st));
@@ -440,10 +443,7 @@ rebuild:
 		}
 	}
 	if (!rc && h_flags[1]) rc = build_lcp_phi(ctx, E);
-	if (!rc) {	// suffix array and prefix lengths are final: the walk's view of the directory
-		k_fast_dir<<<nblocks(kmers, 256), 256, 0, st>>>(E->dir, E->SA, E->plen, E->fdir, (u32)kmers);
-		ctx->st.esa_launches++;
-	}
+	if (!rc) rc = build_prefix_lengths(ctx, E);	 // the suffix array is final
 	return rc;
 }
 

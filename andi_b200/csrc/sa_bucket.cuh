@@ -224,11 +224,10 @@ __global__ void k_padded_place(int K, const u64 *__restrict__ key, const u32 *__
 // separator inside) | their number << 32; first + number = end of the bucket. *n_ambiguous counts the suffixes that are still tied
 // with a neighbour; their groups are materialised by k_bucket_groups only when there are any.
 template <bool SPEC>
-__global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
-							  const u32 *__restrict__ fvalid, u32 *__restrict__ SA, u64 *__restrict__ dir64,
-							  u32 *__restrict__ n_ambiguous, u32 empty_known) {
-	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
-	if (key >= (1u << (2 * K))) return;
+__device__ __forceinline__ u32 bucket_sort_key(const TextView &rs, int K, u32 key, const u32 *__restrict__ bstart,
+											   const u32 *__restrict__ bend, const u32 *__restrict__ fvalid,
+											   u32 *__restrict__ SA, u64 *__restrict__ dir64,
+											   u32 *__restrict__ n_ambiguous, u32 empty_known) {
 	const u32 e = bend[key];
 	// fvalid given: the padded suffixes already stand sorted in [bstart, fvalid) (k_padded_place)
 	const u32 b = fvalid ? min(fvalid[key], e) : bstart[key], s = e - b;
@@ -237,12 +236,12 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 		// end of k-1 (the generic search narrows its range with that). The radix bucketing path
 		// does not know where an empty bucket lies: 0xffffffff = unknown.
 		dir64[key] = empty_known ? (u64)e : 0xffffffffULL;
-		return;
+		return 0;
 	}
 	if (fvalid && s > ANDI_SORT_MAX) {	// valid suffixes only: one group of depth K for the doubling rounds
 		atomicAdd(n_ambiguous, s);
 		dir64[key] = (u64)b | ((u64)s << 32);
-		return;
+		return s;
 	}
 	u32 valid = 0;
 	if (s > ANDI_SORT_MAX) {
@@ -271,14 +270,14 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 		}
 		if (valid > 1) atomicAdd(n_ambiguous, valid);
 		dir64[key] = (u64)front | ((u64)valid << 32);
-		return;
+		return valid;
 	}
 	if (s <= 2) {
 		// nine buckets in ten: one suffix (nothing to order) or two (one comparison decides order
 		// and tie) -- kept out of the local-memory array of the general case
 		if (s == 0) {  // only padded suffixes (already placed)
 			dir64[key] = (u64)e;
-			return;
+			return 0;
 		}
 		u32 p0 = SA[b], p1 = s == 2 ? SA[b + 1] : 0u;
 		valid = fvalid ? s : (u32)!is_padded<SPEC>(rs, p0, K);
@@ -289,7 +288,7 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 			if (c == 0) atomicAdd(n_ambiguous, 2u);
 		}
 		dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
-		return;
+		return valid;
 	}
 	u32 v[ANDI_SORT_MAX];
 #pragma unroll
@@ -313,7 +312,30 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 	}
 	if (tied) atomicAdd(n_ambiguous, tied + 1);
 	dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
+	return valid;
 }
+
+// One thread per k-mer. Besides the directory entry the kernel leaves level K-1 of the
+// presence bitmaps (esa_kernels.cuh): bit y is set iff one of the four k-mers 4y..4y+3 occurs,
+// folded from a warp ballot (the words must be zero before the launch).
+template <bool SPEC>
+__global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
+							  const u32 *__restrict__ fvalid, u32 *__restrict__ SA, u64 *__restrict__ dir64,
+							  u32 *__restrict__ n_ambiguous, u32 empty_known, u32 *__restrict__ present_top) {
+	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 count = 0;
+	if (key < (1u << (2 * K))) count = bucket_sort_key<SPEC>(rs, K, key, bstart, bend, fvalid, SA, dir64, n_ambiguous, empty_known);
+	u32 m = __ballot_sync(0xffffffffu, count != 0);
+	if ((threadIdx.x & 31u) == 0 && m) {
+		m |= m >> 1, m |= m >> 2;  // bit 4g = any of the four k-mers of group g
+		u32 folded = 0;
+#pragma unroll
+		for (int g = 0; g < 8; g++) folded |= ((m >> (4 * g)) & 1u) << g;
+		u32 y0 = key >> 2;	// first (K-1)-mer of this warp (key is a multiple of 32 here)
+		atomicOr(present_top + (y0 >> 5), folded << (y0 & 31u));
+	}
+}
+
 
 // The walk's view of the directory, one 8-byte entry per k-mer so that the common lookups cost
 // ONE table access (the tables compete with the streaming queries for L2):
@@ -322,22 +344,8 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 //   tag 1 (one suffix)      low 32 bits = its text position: the compare starts without the
 //                           dependent suffix-array load
 //   tag 2 (several)         low 32 bits = first SA index, bits 32..61 = their number
+// Written by k_prefix_len (esa_kernels.cuh) together with the prefix lengths.
 #define ANDI_FDIR_TAG(e) ((u32)((e) >> 62))
-__global__ void k_fast_dir(const u64 *__restrict__ dir64, const u32 *__restrict__ SA,
-						   const unsigned char *__restrict__ plen, u64 *__restrict__ fdir, u32 kmers) {
-	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
-	if (key >= kmers) return;
-	u64 de = dir64[key];
-	u32 first = (u32)de, count = (u32)(de >> 32);
-	u64 out;
-	if (count == 0)
-		out = plen[key];
-	else if (count == 1)
-		out = (1ULL << 62) | SA[first];
-	else
-		out = (2ULL << 62) | ((u64)count << 32) | first;
-	fdir[key] = out;
-}
 
 // Only when k_bucket_sort reported ties: group heads, ranks and "ambiguous" flags of every
 // suffix, the input of the doubling rounds (index_host.cuh). Buckets are laid out as
