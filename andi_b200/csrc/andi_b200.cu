@@ -77,7 +77,7 @@ struct andi_esa {
 	u64 *dir = nullptr;
 	PresenceLevels present{};
 	unsigned char *plen = nullptr;
-	u64 *fdir = nullptr;  // 4^K: the walk's own view of the directory (k_fast_dir)
+	u64 *fdir = nullptr;  // 4^K: the walk's own view of the directory (written by k_prefix_len)
 	int K = 0;
 	bool has_sep = false;
 	bool full = false;

@@ -32,7 +32,7 @@ struct SubjectIndex {
 	const int32_t *LCP;	   // N + 1
 	const u64 *dir;		   // 4^K: first SA index | count << 32 of every k-mer
 	const unsigned char *plen;  // 4^K: longest prefix of each k-mer present in RS (< K)
-	const u64 *fdir;	   // 4^K: the phase-pipeline kernels' view of dir / plen / SA (k_fast_dir)
+	const u64 *fdir;	   // 4^K: the phase-pipeline kernels' view of dir / plen / SA (k_prefix_len)
 	int K;				   // directory depth, 0 = none (lookups use the generic search only)
 	u32 threshold;		   // minimum anchor length for this subject
 	u32 self;			   // pool index of the subject (its own query is skipped)
