@@ -4,8 +4,9 @@
 // Same units, same records, same results as k_walk_chunks<QUARTER, SPEC>. QUARTER = RAW / JC /
 // KIMURA counting without separators is the headline configuration; !QUARTER (LOGDET / ANI)
 // needs the pool's prefix-composition table; SPEC (join mode, '!' in subject or queries) reads
-// the spec planes next to the code planes. What changes
-// is the execution shape. In the straightforward kernel every lane runs nested while-loops
+// the spec planes next to the code planes where a hint byte says a separator is near.
+//
+// What changes is the execution shape. In the straightforward kernel every lane runs nested while-loops
 // (window compares of different lengths, bucket scans, bitmap probes) and the warp waits for
 // its slowest lane at every level: ncu showed 6 of 32 lanes active. A pure lane-level state
 // machine (one op per lane per trip) does not fix that either: lanes drift apart and every
@@ -24,8 +25,10 @@
 //
 //   BEGIN   chunk/phase bookkeeping, then set up the lucky compare (process.c:86-99)
 //   CMP     one 64-base window of a compare (lucky diagonal or directory candidate)
-//   DIR     k-mer directory + prefix-length probe      CAND   fetch SA[candidate]
-//   SLOW    anything unusual -> longest_match<false>() of walk_kernels.cuh
+//   DIR     one load from the directory view fdir: absent k-mer -> its prefix length, done;
+//           one suffix -> its text position, compare it in this trip; several -> CAND
+//   CAND    fetch SA[candidate] (buckets with several suffixes, and their later candidates)
+//   SLOW    anything unusual -> longest_match<SPEC>() of walk_kernels.cuh
 //   DECIDE  process.c:160-196: pairing, accounting, advance
 //   COLS    classify up to 16 gap columns (model.c:309-337)
 //
