@@ -1,0 +1,30 @@
+"""The committed bench line (profiles/r1_bench_n1.json, written by bench.py on a B200) carries
+every key of the measurement contract, and its derived numbers are consistent."""
+import json
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    d = json.loads((ROOT / "profiles" / "r1_bench_n1.json").read_text())
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "pairs/s" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
+    assert d["gpu_launches"] > 0
+    e = d["e2e"]
+    assert e["unit"] == "pairs/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    # achieved = algorithmic bytes per launch / average launch duration
+    want = r["pairs_per_launch"] * r["algorithmic_bytes_per_pair"] / (r["launch_ms"] * 1e-3) / 1e9
+    assert abs(r["achieved"] - want) / want < 1e-6
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "pairs/s" and c["sample"]
+    # value = pairs of the timed region / its duration
+    pairs = d["config"]["pairs_per_step"]
+    assert abs(d["value"] - pairs / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
