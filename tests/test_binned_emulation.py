@@ -1,0 +1,140 @@
+"""Round-2 groundwork: the phase-binned walk kernel (andi_b200/csrc/experimental/) is not part of
+the library yet, but its per-unit phase logic is already checked here on the CPU. The phases
+header compiles both into the CUDA kernel and into a serial host emulation (emu_binned.cpp);
+this test builds the index with numpy from the oracle's suffix array, runs the emulation (same
+queues, same super-steps, one unit at a time), reduces its records the way k_walk_reduce does
+and compares with the oracle. Test infrastructure only; nothing here touches a GPU."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from andi_b200 import synth
+
+ROOT = Path(__file__).resolve().parent.parent
+EXP = ROOT / "andi_b200" / "csrc" / "experimental"
+UNIT_WORDS = 38
+CODE = np.full(256, 255, dtype=np.uint8)
+for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3), (b"#", 1)):
+    CODE[ch[0]] = v
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = EXP / "libemu_binned.so"
+    src = [EXP / "emu_binned.cpp", EXP / "walk_binned_phases.h"]
+    if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src[0])], check=True,
+                       cwd=EXP, capture_output=True)
+    L = C.CDLL(str(so))
+    L.emu_walk_binned.restype = C.c_long
+    L.emu_walk_binned.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    return L
+
+
+def pack(text: bytes) -> np.ndarray:
+    """text.cuh: 2 bits per character, 32 characters per u64 word, four zero guard words."""
+    codes = CODE[np.frombuffer(text, dtype=np.uint8)].astype(np.uint64)
+    assert (codes < 4).all()
+    words = len(text) // 32 + 4
+    padded = np.zeros(words * 32, dtype=np.uint64)
+    padded[: len(text)] = codes
+    shifts = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, :]
+    return (padded.reshape(words, 32) << shifts).sum(axis=1, dtype=np.uint64)
+
+
+def directory_view(rs: bytes, SA: np.ndarray, K: int) -> np.ndarray:
+    """fdir of sa_bucket.cuh / esa_kernels.cuh, restated with numpy: per k-mer tag 0 + longest
+    present prefix / tag 1 + text position of its only suffix / tag 2 + first SA index, count."""
+    N, mid = len(rs), len(rs) // 2
+    codes = CODE[np.frombuffer(rs, dtype=np.uint8)].astype(np.int64)
+    pos = np.arange(N)
+
+    def mers(m):  # key of the m-mer at every position where it lies inside the text and off '#'
+        ok = (pos + m <= N) & ~((pos <= mid) & (mid < pos + m))
+        key = np.zeros(N, dtype=np.int64)
+        for c in range(m):
+            key = key * 4 + np.where(pos + c < N, codes[np.minimum(pos + c, N - 1)], 0)
+        return ok, key
+
+    ok, key = mers(K)
+    rank = np.empty(N, dtype=np.int64)
+    rank[SA] = np.arange(N)
+    count = np.bincount(key[ok], minlength=4**K)
+    first = np.full(4**K, N, dtype=np.int64)
+    np.minimum.at(first, key[ok], rank[ok])
+    # the valid suffixes of a k-mer are contiguous in SA
+    last = np.zeros(4**K, dtype=np.int64)
+    np.maximum.at(last, key[ok], rank[ok])
+    present = count > 0
+    assert (last[present] - first[present] + 1 == count[present]).all()
+    plen = np.zeros(4**K, dtype=np.int64)
+    for m in range(1, K):
+        okm, keym = mers(m)
+        have = np.bincount(keym[okm], minlength=4**m) > 0
+        prefix = np.arange(4**K) >> (2 * (K - m))
+        plen = np.where(have[prefix], m, plen)
+    fdir = np.where(count == 0, plen, 0).astype(np.uint64)
+    one = count == 1
+    fdir[one] = (np.uint64(1) << np.uint64(62)) | SA[first[one]].astype(np.uint64)
+    many = count > 1
+    fdir[many] = (np.uint64(2) << np.uint64(62)) | (count[many].astype(np.uint64) << np.uint64(32)) | first[many].astype(np.uint64)
+    return fdir
+
+
+def reduce_records(rec: np.ndarray, qlens, chunk: int, cpq: int, threshold: int, skip: int) -> np.ndarray:
+    """k_walk_reduce for records whose boundaries all synchronised, plus walk_tail
+    (src/process.c:199-211) with the len/4 split of src/model.c:247-254."""
+    out = np.zeros((len(qlens), 17), dtype=np.uint32)
+    for k, qlen in enumerate(qlens):
+        if k == skip:
+            out[k, 0] = out[k, 16] = 9  # src/dist_hack.h:61-64
+            continue
+        nch = -(-qlen // chunk)
+        r = rec[k * cpq : k * cpq + nch].astype(np.int64)
+        assert (r[:-1, 37] == 1).all(), "a chunk boundary did not synchronise: needs the sequential path of k_walk_reduce"
+        total = r[:, :16].sum(axis=0) + r[:-1, 16:32].astype(np.int32).sum(axis=0)
+        last_len, paired = int(r[-1, 35]), int(r[-1, 36])
+        tail = qlen if last_len >= qlen else (last_len if (paired or last_len >= 2 * threshold) else 0)
+        for cell in (0, 5, 10):
+            total[cell] += tail // 4
+        total[15] += tail // 4 + tail % 4
+        out[k, :16] = total.astype(np.uint32)
+        out[k, 16] = qlen
+    return out
+
+
+# (repeat-rich texts and anchors longer than a chunk leave chunk boundaries unsynchronised; that path belongs to k_walk_reduce,
+# not to the kernel emulated here, so those sets run with one chunk per query)
+@pytest.mark.parametrize("name,chunk", [("subst", 1000), ("subst", 4096), ("indel", 700), ("repeat", 1 << 20),
+                                        ("identical", 1 << 20), ("lowent", 1 << 20), ("short", 1 << 20), ("unrelated", 1 << 20),
+                                        ("revcomp", 2048)])
+def test_binned_phases_match_the_oracle(emu, name, chunk):
+    from conftest import stress_sequences
+
+    seqs = [s for s in stress_sequences()[name] if b"!" not in s]
+    want = oracle.rows(seqs, "JC")
+    qplanes = [pack(s) for s in seqs]
+    q_off = np.cumsum([0] + [len(p) for p in qplanes[:-1]]).astype(np.uint64)
+    pool = np.concatenate(qplanes)
+    q_len = np.array([len(s) for s in seqs], dtype=np.uint32)
+    cpq = max(1, -(-int(q_len.max()) // chunk))
+    for i, subject in enumerate(seqs):
+        o = oracle.OracleEsa(subject)
+        rs, SA = o.rs, o.array("SA").astype(np.uint32)
+        N = len(rs)
+        t = int(oracle.lib().orc_min_anchor_length(0.025, oracle.lib().orc_gc(subject, len(subject)), N))
+        K = min(t, max(4, round(np.log(N) / np.log(4))))
+        s_code, fdir = pack(rs), directory_view(rs, SA, K)
+        rec = np.zeros((len(seqs) * cpq, UNIT_WORDS), dtype=np.uint32)
+        stats = np.zeros(14, dtype=np.uint64)
+        steps = emu.emu_walk_binned(s_code.ctypes.data, N, N // 2, SA.ctypes.data, fdir.ctypes.data, K, i, t, pool.ctypes.data,
+                                    q_off.ctypes.data, q_len.ctypes.data, len(seqs), chunk, cpq, rec.ctypes.data, stats.ctypes.data)
+        assert steps > 0
+        got = reduce_records(rec, [int(x) for x in q_len], chunk, cpq, t, skip=i)
+        assert np.array_equal(got, want[i]), (name, i, chunk, stats.tolist())
+        o.close()
