@@ -6,6 +6,9 @@
 // splitting every query into chunks (walk_kernels.cuh).
 #pragma once
 #include "walk_fast.cuh"
+#ifdef ANDI_EXPERIMENTAL_BINNED	 // development builds only (see experimental/walk_binned.cuh); never set by the Makefile
+#include "experimental/walk_binned.cuh"
+#endif
 
 typedef void (*chunks_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, u32 *,
 						  unsigned long long *);
@@ -113,6 +116,14 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	}
 	if (!ctx->walk_counter) CK(dalloc(ctx, &ctx->walk_counter, 1));
 	CK(cudaMemsetAsync(ctx->walk_counter, 0, sizeof(unsigned long long), ctx->stream));
+#ifdef ANDI_EXPERIMENTAL_BINNED
+	if (force && strcmp(force, "binned") == 0 && quarter && !spec && S.K > 0 && units < 0xffffffffULL &&
+		(pool_queries || S.qcode_base)) {
+		if (pool_queries) S.qcode_base = ctx->pool_code;
+		CK(launch_walk_binned(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records, ctx->walk_counter,
+							  ctx->sm_count, ctx->stream));
+	} else
+#endif
 	cf<<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
 													 d_records, ctx->walk_counter);
 	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
