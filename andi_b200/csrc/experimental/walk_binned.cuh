@@ -1,9 +1,12 @@
 // andi_b200/csrc/experimental/walk_binned.cuh -- EXPERIMENTAL, NOT PART OF THE LIBRARY.
 //
 // Round-2 groundwork for the anchor walk: the phase-binned form of k_walk_chunks_fast<1,0>
-// (RAW / JC / KIMURA counting, no separators). It is compiled by `make experimental` only as a
-// syntax / ptxas check; it has not run on a GPU yet, no parity is claimed and nothing in
-// libandi_b200.so refers to it. DESIGN.md section 4 ("Round-2 plan") says why it exists.
+// (RAW / JC / KIMURA counting, no separators). `make experimental` compiles it as a syntax /
+// ptxas check; libandi_b200.so does not contain it (a development build with
+// -DANDI_EXPERIMENTAL_BINNED launches it through ANDI_B200_WALK=binned). Status at the end of
+// round 1: the phase logic passes tests/test_binned_emulation.py on the CPU and one GPU run gave
+// rows equal to the oracle on five stress groups, but this untuned form is 3.5x slower than
+// k_walk_chunks_fast -- see DESIGN.md section 4 ("Round-2 plan") for the numbers and the reasons.
 //
 // The measured problem of k_walk_chunks_fast (profiles/r1j_*): a warp executes every phase of a
 // trip for the 10-18 of its 32 lanes that need it (13.6 lanes per instruction on average), and
