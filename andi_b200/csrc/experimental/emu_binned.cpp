@@ -38,6 +38,7 @@ struct QueryView {
 #define ANDI_SCAN_MAX 8
 #define ANDI_FDIR_TAG(e) ((u32)((e) >> 62))
 #define BIN_FN static inline
+#define BIN_OUTLINE_FN static
 
 // ---- primitives
 static inline u64 bin_ld64(const u64 *p) { return *p; }

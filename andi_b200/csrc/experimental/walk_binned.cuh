@@ -40,6 +40,7 @@
 
 // ---- the primitives of walk_binned_phases.h on the device
 #define BIN_FN __device__ __forceinline__
+#define BIN_OUTLINE_FN __device__ __noinline__
 __device__ __forceinline__ u64 bin_ld64(const u64 *p) { return __ldg(p); }
 __device__ __forceinline__ u32 bin_ld32(const u32 *p) { return __ldg(p); }
 __device__ __forceinline__ u32 bin_ffs64(u64 x) { return (u32)(__ffsll((long long)x) - 1); }

@@ -4,7 +4,7 @@
 // the SAME text compiles into the CUDA kernel (walk_binned.cuh) and into a serial host emulation
 // (emu_binned.cpp, driven by tests/test_binned_emulation.py against the oracle). Whoever includes
 // this file provides:
-//   BIN_FN                                  function qualifier
+//   BIN_FN, BIN_OUTLINE_FN                  function qualifiers (inlined / one out-of-line copy)
 //   SubjectIndex / QueryView / TextView      with the field names of walk_kernels.cuh
 //   window64, window16, kmer_key             as in text.cuh
 //   bin_ld64, bin_ld32                       read-only loads
@@ -67,7 +67,8 @@ struct BinConst {
 
 // src/process.c:86-99 and the chunk / boundary-replay bookkeeping of walk_fast.cuh's BEGIN.
 // Returns the queue the slot goes to (BQ_CMP, or BQ_FETCH once the unit's record is written).
-BIN_FN u32 bin_begin(BinShared &sh, u32 s, const BinConst &c, u32 *__restrict__ records) {
+// (one out-of-line copy: FETCH, DECIDE and COLS all end in it, and it holds the 38-word record write)
+BIN_OUTLINE_FN u32 bin_begin(BinShared &sh, u32 s, const BinConst &c, u32 *__restrict__ records) {
 	u32 fl = sh.flags[s];
 	u32 a_pos = sh.a_pos[s], a_ls = sh.a_ls[s], a_lq = sh.a_lq[s], a_ll = sh.a_ll[s], a_pm = sh.a_pm[s];
 	const u32 qlen = sh.qlen[s], c_end = sh.c_end[s];
