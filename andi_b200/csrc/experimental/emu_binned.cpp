@@ -92,11 +92,17 @@ static inline void bin_slow_lookup(const SubjectIndex &S, const u64 *q_code, u32
 
 extern "C" int emu_binned_slots(void) { return ANDI_BIN_SLOTS; }
 
-// Returns the number of super-steps, or -1 on bad arguments. stats[q] += units processed in phase q,
+static u64 emu_rand(u64 &x) {  // xorshift64*
+	x ^= x >> 12, x ^= x << 25, x ^= x >> 27;
+	return x * 0x2545F4914F6CDD1DULL;
+}
+
+// seed == 0: the kernel's lock-step super-steps; seed != 0: a random asynchronous order.
+// Returns the number of super-steps (batches for seed != 0), or -1 on bad arguments. stats[q] += units processed in phase q,
 // stats[BQ_N + q] += 32-lane batches a CTA would have issued for them (ceil per queue and super-step).
 extern "C" long emu_walk_binned(const u64 *s_code, u32 N, u32 mid, const u32 *SA, const u64 *fdir, int K, u32 self,
 								u32 threshold, const u64 *pool_code, const u64 *q_word_off, const u32 *q_len, u32 nq,
-								u32 chunk, u32 cpq, u32 *records, u64 *stats) {
+								u32 chunk, u32 cpq, u32 *records, u64 *stats, u64 seed) {
 	if (!s_code || !SA || !fdir || !pool_code || !records || K <= 0 || (u64)nq * cpq >= 0xffffffffULL) return -1;
 	SubjectIndex S;
 	S.rs.code = s_code, S.rs.spec = nullptr, S.rs.len = N, S.rs.mid = mid;
@@ -117,6 +123,35 @@ extern "C" long emu_walk_binned(const u64 *s_code, u32 N, u32 mid, const u32 *SA
 	sh.count[0][BQ_FETCH] = ANDI_BIN_SLOTS;
 	u32 cur = 0, waited[BQ_N] = {0};
 	long steps = 0;
+	if (seed) {
+		// Asynchronous order: the phase logic must not depend on the lock-step schedule (a later
+		// kernel lets warps pull batches independently). One queue set; repeatedly take a random
+		// number of units off the front of a random non-empty queue and run them, pushing straight
+		// back into the same set (as ring buffers would).
+		u64 rng = seed;
+		std::vector<std::vector<unsigned short>> ring(BQ_N);
+		for (u32 t = 0; t < ANDI_BIN_SLOTS; t++) ring[BQ_FETCH].push_back((unsigned short)t);
+		for (;;) {
+			u32 nonempty = 0;
+			for (u32 q = 0; q < BQ_N; q++) nonempty += !ring[q].empty();
+			if (!nonempty) break;
+			u32 q;
+			do q = (u32)(emu_rand(rng) % BQ_N);
+			while (ring[q].empty());
+			u32 take = 1 + (u32)(emu_rand(rng) % 32);
+			if (take > ring[q].size()) take = (u32)ring[q].size();
+			std::vector<unsigned short> batch(ring[q].begin(), ring[q].begin() + take);
+			ring[q].erase(ring[q].begin(), ring[q].begin() + take);
+			for (u32 x = 0; x < BQ_N; x++) sh.count[0][x] = 0;
+			for (unsigned short s : batch) bin_phase(q, s, sh, 0, S, queries.data(), nullptr, c, total, records, &next_unit);
+			for (u32 x = 0; x < BQ_N; x++)
+				for (u32 y = 0; y < sh.count[0][x]; y++) ring[x].push_back(sh.queue[0][x][y]);
+			if (stats) stats[q] += take, stats[BQ_N + q] += 1;
+			steps++;
+		}
+		delete shp;
+		return steps;
+	}
 	for (;;) {
 		u32 pending = 0;
 		for (u32 q = 0; q < BQ_N; q++) pending += sh.count[cur][q];

@@ -32,7 +32,7 @@ def emu():
     L = C.CDLL(str(so))
     L.emu_walk_binned.restype = C.c_long
     L.emu_walk_binned.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
-                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
     return L
 
 
@@ -113,7 +113,8 @@ def reduce_records(rec: np.ndarray, qlens, chunk: int, cpq: int, threshold: int,
 @pytest.mark.parametrize("name,chunk", [("subst", 1000), ("subst", 4096), ("indel", 700), ("repeat", 1 << 20),
                                         ("identical", 1 << 20), ("lowent", 1 << 20), ("short", 1 << 20), ("unrelated", 1 << 20),
                                         ("revcomp", 2048)])
-def test_binned_phases_match_the_oracle(emu, name, chunk):
+@pytest.mark.parametrize("seed", [0, 12345])  # 0: the kernel's lock-step super-steps; else: a random asynchronous order
+def test_binned_phases_match_the_oracle(emu, name, chunk, seed):
     from conftest import stress_sequences
 
     seqs = [s for s in stress_sequences()[name] if b"!" not in s]
@@ -133,8 +134,8 @@ def test_binned_phases_match_the_oracle(emu, name, chunk):
         rec = np.zeros((len(seqs) * cpq, UNIT_WORDS), dtype=np.uint32)
         stats = np.zeros(14, dtype=np.uint64)
         steps = emu.emu_walk_binned(s_code.ctypes.data, N, N // 2, SA.ctypes.data, fdir.ctypes.data, K, i, t, pool.ctypes.data,
-                                    q_off.ctypes.data, q_len.ctypes.data, len(seqs), chunk, cpq, rec.ctypes.data, stats.ctypes.data)
+                                    q_off.ctypes.data, q_len.ctypes.data, len(seqs), chunk, cpq, rec.ctypes.data, stats.ctypes.data, seed)
         assert steps > 0
         got = reduce_records(rec, [int(x) for x in q_len], chunk, cpq, t, skip=i)
-        assert np.array_equal(got, want[i]), (name, i, chunk, stats.tolist())
+        assert np.array_equal(got, want[i]), (name, i, chunk, seed, stats.tolist())
         o.close()
