@@ -264,8 +264,8 @@ __global__ void k_presence_patch(TextView rs, int K, PresenceLevels lv, u32 firs
 // what a lookup of an ABSENT k-mer returns. It does not depend on the last character, so one
 // thread serves the four k-mers 4y..4y+3 of a (K-1)-mer y: one probe sequence, one 32-byte
 // directory read, and the four entries of the walk's own directory view (fdir, see
-// sa_bucket.cuh: tag 0 + plen / tag 1 + text position of the only suffix / tag 2 + first index
-// and count) in the same pass. Runs once the suffix array is final.
+// sa_bucket.cuh: tag 0 + plen / tag 1 + text position of the only suffix / tag 2 + the text positions of
+// both suffixes / tag 3 + first index and count) in the same pass. Runs once the suffix array is final.
 __global__ void k_prefix_len(PresenceLevels lv, int K, const u64 *__restrict__ dir, const u32 *__restrict__ SA,
 							 unsigned char *__restrict__ plen, u64 *__restrict__ fdir) {
 	u32 y = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,8 +289,10 @@ __global__ void k_prefix_len(PresenceLevels lv, int K, const u64 *__restrict__ d
 			out[c] = l;
 		else if (count == 1)
 			out[c] = (1ULL << 62) | SA[first];
+		else if (count == 2)
+			out[c] = (2ULL << 62) | ((u64)SA[first + 1] << 31) | SA[first];
 		else
-			out[c] = (2ULL << 62) | ((u64)count << 32) | first;
+			out[c] = (3ULL << 62) | ((u64)count << 32) | first;
 	}
 	ulonglong2 *dout = reinterpret_cast<ulonglong2 *>(fdir) + 2 * (size_t)y;
 	dout[0] = make_ulonglong2(out[0], out[1]);

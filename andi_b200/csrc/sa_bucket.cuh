@@ -343,7 +343,9 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 //                           is all the walk needs (no anchor can result below K)
 //   tag 1 (one suffix)      low 32 bits = its text position: the compare starts without the
 //                           dependent suffix-array load
-//   tag 2 (several)         low 32 bits = first SA index, bits 32..61 = their number
+//   tag 2 (two suffixes)    bits 0..30 and 31..61 = their text positions in suffix order (N < 2^31):
+//                           most buckets with company hold exactly two, no suffix-array load either
+//   tag 3 (three or more)   low 32 bits = first SA index, bits 32..61 = their number
 // Written by k_prefix_len (esa_kernels.cuh) together with the prefix lengths.
 #define ANDI_FDIR_TAG(e) ((u32)((e) >> 62))
 

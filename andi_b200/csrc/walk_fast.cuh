@@ -276,7 +276,9 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 				C.cs = p, C.ck = 0, C.clim = min(rem, run), C.is_cand = 1;
 				op = OP_CMP;
 			} else {
-				u32 t0 = (u32)fe, cnt = (u32)(fe >> 32) & 0x3fffffffu;
+				// two or more suffixes: this kernel walks them through the suffix array
+				u64 de = __ldg(S.dir + L.key);
+				u32 t0 = (u32)de, cnt = (u32)(de >> 32);
 				if (cnt <= ANDI_SCAN_MAX) {
 					L.cand = t0, L.hi = t0 + cnt;
 					op = OP_CAND;

@@ -6,9 +6,7 @@
 // splitting every query into chunks (walk_kernels.cuh).
 #pragma once
 #include "walk_fast.cuh"
-#ifdef ANDI_EXPERIMENTAL_BINNED	 // development builds only (see experimental/walk_binned.cuh); never set by the Makefile
-#include "experimental/walk_binned.cuh"
-#endif
+#include "walk_v3.cuh"
 
 typedef void (*chunks_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, u32 *,
 						  unsigned long long *);
@@ -102,8 +100,14 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 			cf = spec ? k_walk_chunks_fast<false, true> : k_walk_chunks_fast<false, false>;
 		}
 	}
+	// the headline configuration goes through k_walk_v3 (walk_v3.cuh): PHASE 1 over all units,
+	// PHASE 2 over all chunk boundaries; ANDI_B200_WALK=pipeline keeps the round-1 kernel
+	const bool v3 = quarter && !spec && v3_applies(S, threshold) && !(force && (strcmp(force, "basic") == 0 || strcmp(force, "pipeline") == 0));
 	int per_sm = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf, ANDI_WALK_THREADS, 0));
+	if (v3)
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_v3<1>, ANDI_WALK_THREADS, 0));
+	else
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf, ANDI_WALK_THREADS, 0));
 	if (per_sm < 1) per_sm = 1;
 	unsigned long long units = (unsigned long long)nq * plan.cpq;
 	unsigned grid = (unsigned)std::min<unsigned long long>((units + ANDI_WALK_THREADS - 1) / ANDI_WALK_THREADS,
@@ -114,18 +118,19 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 		ctx->first_ev = get_event(ctx);
 		mark(ctx, ctx->first_ev);
 	}
-	if (!ctx->walk_counter) CK(dalloc(ctx, &ctx->walk_counter, 1));
-	CK(cudaMemsetAsync(ctx->walk_counter, 0, sizeof(unsigned long long), ctx->stream));
-#ifdef ANDI_EXPERIMENTAL_BINNED
-	if (force && strcmp(force, "binned") == 0 && quarter && !spec && S.K > 0 && units < 0xffffffffULL &&
-		(pool_queries || S.qcode_base)) {
-		if (pool_queries) S.qcode_base = ctx->pool_code;
-		CK(launch_walk_binned(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records, ctx->walk_counter,
-							  ctx->sm_count, ctx->stream));
-	} else
-#endif
-	cf<<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
-													 d_records, ctx->walk_counter);
+	if (!ctx->walk_counter) CK(dalloc(ctx, &ctx->walk_counter, 2));
+	CK(cudaMemsetAsync(ctx->walk_counter, 0, 2 * sizeof(unsigned long long), ctx->stream));
+	if (v3) {
+		k_walk_v3<1><<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
+																   d_records, ctx->walk_counter);
+		if (plan.cpq > 1)
+			k_walk_v3<2><<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
+																	   d_records, ctx->walk_counter + 1);
+		ctx->st.walk_launches += plan.cpq > 1 ? 1 : 0;
+	} else {
+		cf<<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
+														 d_records, ctx->walk_counter);
+	}
 	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
 												   d_records, d_out);
 	mark(ctx, e1);

@@ -1,0 +1,106 @@
+// andi_b200/csrc/walk_v3.cuh -- k_walk_v3<PHASE>: the chunked anchor walk for RAW / JC / KIMURA
+// counting without separators (the headline configuration). The per-lane logic, its rationale and
+// its reference citations are in walk_v3_lane.h (the same text runs in the CPU emulation of
+// emu/emu_v3.cpp); this file supplies the device primitives, the warp loop and the launch.
+//
+//   PHASE 1  every (query, chunk) unit from the amnesic state: record words [0,16) U_c, [32,37) E_c
+//   PHASE 2  every chunk boundary: the true chain (from E_c) against the amnesic walk of the next
+//            chunk until both are in the same state: record words [16,32) D_c, [37] flag
+// k_walk_reduce (walk_kernels.cuh) then sums the records exactly as it does for k_walk_chunks.
+#pragma once
+#include "walk_kernels.cuh"
+
+#define V3_FN __device__ __forceinline__
+#define V3_THREADS ANDI_WALK_THREADS
+#define V3_CELL_STRIDE V3_THREADS
+#ifndef V3_SERVE_BATCH
+#define V3_SERVE_BATCH 6u  // parked lanes that make a warp stop and serve them ...
+#endif
+#ifndef V3_SERVE_EVERY
+#define V3_SERVE_EVERY 8u  // ... or every so many trips (a power of two)
+#endif
+#ifndef V3_BLOCKS_PER_SM
+#define V3_BLOCKS_PER_SM 4
+#endif
+#define V3_STAT(name) \
+	do {              \
+	} while (0)
+
+V3_FN u32 v3_ctz64(u64 x) { return (u32)(__ffsll((long long)x) - 1); }
+V3_FN u32 v3_popc64(u64 x) { return (u32)__popcll(x); }
+V3_FN u64 v3_ld_fdir(const u64 *p) { return __ldg(p); }
+V3_FN void v3_window64(const u64 *__restrict__ w, u32 pos, u64 &lo, u64 &hi) { window64(w, pos, lo, hi); }
+V3_FN u32 v3_kmer_key(u64 win, int k) { return kmer_key(win, k); }
+
+#include "walk_v3_lane.h"
+
+// The generic step (walk_step of walk_kernels.cuh) for the few lanes the window jobs do not
+// cover; a real call, so its registers do not weigh on the main loop.
+__device__ __noinline__ void v3_slow_step(const SubjectIndex &S, u32 t, const u64 *q_code, u32 qlen, u32 *col, u32 sign,
+										  u32 &pos, u32 &ls, u32 &lq, u32 &ll, u32 &paired) {
+	TextView q;
+	q.code = q_code, q.spec = nullptr, q.len = qlen, q.mid = 0xffffffffu;
+	WalkState w;
+	w.pos_q = pos, w.last_s = ls, w.last_q = lq, w.last_len = ll, w.paired = paired;
+	SharedAcc acc = {col, sign};
+	walk_step<true, false>(S, q, t, w, acc);
+	pos = w.pos_q, ls = w.last_s, lq = w.last_q, ll = w.last_len, paired = w.paired;
+}
+
+struct V3Env {
+	const SubjectIndex &S;
+	u64 total;
+	u32 *records;
+	unsigned long long *counter;
+	const QueryView *queries;
+	const u32 *query_ids;
+	u32 t;
+	__device__ __forceinline__ u64 next_unit() { return atomicAdd(counter, 1ULL); }
+	template <int PHASE>
+	__device__ __forceinline__ bool open_unit(u64 unit, V3Lane &L, const V3Const &c, u32 *col) {
+		u32 k, ch;
+		v3_split_unit(unit, total, c.cpq, k, ch);
+		const u32 qid = query_ids ? query_ids[k] : k;
+		if (qid == S.self) return false;
+		return v3_begin_unit<PHASE>(L, c, queries[qid].t.code, queries[qid].t.len, ch, records + unit * ANDI_UNIT_WORDS, col);
+	}
+	__device__ __forceinline__ void slow_step(V3Lane &L, u32 *col, u32 sign) {
+		// (copies: a lane field whose address escapes into the call would live in local memory)
+		u32 pos = L.pos, ls = L.ls, lq = L.lq, ll = L.ll, paired = L.paired;
+		v3_slow_step(S, t, L.q_code, L.qlen, col, sign, pos, ls, lq, ll, paired);
+		L.pos = pos, L.ls = ls, L.lq = lq, L.ll = ll, L.paired = paired;
+	}
+};
+
+template <int PHASE>
+__global__ void __launch_bounds__(V3_THREADS, V3_BLOCKS_PER_SM)
+k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 nq, u32 chunk,
+		  u32 cpq, u32 threshold, u32 *__restrict__ records, unsigned long long *__restrict__ next_unit) {
+	__shared__ u32 cells[16][V3_THREADS];
+	u32 *col = &cells[0][threadIdx.x];
+	V3Const c;
+	c.t = threshold, c.N = S.rs.len, c.mid = S.rs.mid, c.border = S.rs.len / 2, c.chunk = chunk, c.cpq = cpq, c.K = S.K;
+	c.s_code = S.rs.code, c.fdir = S.fdir;
+	V3Env env = {S, (u64)nq * cpq, records, next_unit, queries, query_ids, threshold};
+	V3Lane L;
+	L.svc = V3_SVC_FETCH, L.job = V3_STEP;
+	L.pos = L.ls = L.lq = L.ll = L.paired = L.cand_p = L.cand2 = L.len1 = L.sumq = L.sumr = 0;
+	L.q_code = nullptr, L.qlen = 0, L.c_end = 0, L.unit = 0;
+	L.b_pos = L.b_ls = L.b_lq = L.b_ll = L.b_paired = 0, L.a_true = 1, L.flag = 1;
+	for (u32 trip = 0;; trip++) {
+		const unsigned parked = __ballot_sync(0xffffffffu, L.svc != V3_RUN && L.svc != V3_SVC_DONE);
+		const unsigned running = __ballot_sync(0xffffffffu, L.svc == V3_RUN);
+		if (!(parked | running)) break;
+		if (v3_serve_now((u32)__popc(parked), (u32)__popc(running), trip)) {
+			if (L.svc != V3_RUN && L.svc != V3_SVC_DONE) v3_service<PHASE>(L, c, env, col);
+			__syncwarp();
+		}
+		if (L.svc == V3_RUN) v3_trip<PHASE>(L, c, col);
+		__syncwarp();
+	}
+}
+
+// Can this walk go through k_walk_v3? (else: k_walk_chunks_fast)
+static inline bool v3_applies(const SubjectIndex &S, u32 threshold) {
+	return S.K > 0 && threshold <= V3_MAX_T && (u32)S.K <= threshold && S.fdir != nullptr;
+}

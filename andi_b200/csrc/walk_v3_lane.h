@@ -1,0 +1,350 @@
+// andi_b200/csrc/walk_v3_lane.h -- per-lane logic of the round-2 anchor-walk kernels
+// (k_walk_v3, walk_v3.cuh). Compiles twice from this one text: into the CUDA kernels (nvcc) and
+// into the serial warp emulation of emu/emu_v3.cpp (g++; tests/test_walk_v3_emulation.py), so the
+// state machine is checked against the oracle on the CPU before it meets a GPU.
+//
+// Same units, same records, same results as k_walk_chunks (walk_kernels.cuh): one lane walks one
+// (query, chunk) unit through the loop of src/process.c:153-197. What changes against the phase
+// pipeline of round 1 (13.6 of 32 lanes active, ~440 thread instructions per walk step):
+//
+//  * ONE trip of the main loop = ONE window job for every running lane, the same straight-line
+//    code for all of them: load 64 columns of query and subject, XOR, find the first mismatch,
+//    act. A job is STEP (start of a walk step: the lucky diagonal of src/process.c:82-100), EXT
+//    (an anchor longer than the window keeps growing) or CAND (the only suffix that carries the
+//    query's k-mer, from the directory view fdir). 93 % of all walk steps end in their first trip.
+//  * The lucky window starts at the END OF THE PREVIOUS ANCHOR, not at pos_Q: the gap columns that
+//    src/model.c:309-337 classifies when the new anchor pairs with the last one are the low
+//    columns of the very window the compare has just loaded. No COLS phase, no second memory
+//    round, no remembered mismatch class.
+//  * Anchor interiors (src/model.c:247-254: len/4 to each diagonal cell, remainder to TtoT) go
+//    to two registers (sum of len>>2, sum of len&3), not to four shared-memory cells.
+//  * The boundary replay (the true chain entering chunk c+1 against that chunk's amnesic walk) is
+//    a SEPARATE LAUNCH (PHASE 2) over the same code: no lane of the main launch carries the
+//    second chain or tests for it.
+//  * Everything rare -- fetching a unit, writing its record, buckets with several suffixes,
+//    query tails shorter than K, an ESA anchor that pairs (gap columns not in registers) -- is
+//    a SERVICE request: the lane parks, and the warp serves parked lanes together once enough
+//    of them wait (or every few trips), so the rare code runs with several lanes instead of one.
+//    The slow step itself is walk_step<>() of walk_kernels.cuh, the proven generic form.
+//
+// QUARTER (RAW / JC / KIMURA) without separators only; the other three instantiations stay with
+// k_walk_chunks_fast.
+#pragma once
+
+#ifndef V3_FN
+#error "define V3_FN and the v3_* primitives before including walk_v3_lane.h"
+#endif
+
+enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V3_SVC_DONE = 4 };
+enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND = 3, V3_CAND1 = 4, V3_CAND2 = 5 };
+
+#define V3_EVEN 0x5555555555555555ULL
+#define V3_MAX_T 31u  // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
+
+struct V3Const {
+	u32 t, N, mid, border, chunk, cpq;
+	int K;
+	const u64 *s_code;
+	const u64 *fdir;
+};
+
+// Chain A is the one being advanced. PHASE 2 carries a second chain B and `a_true` (A is the
+// true chain / the amnesic one); `sign` (+1 / -1 as u32) follows a_true.
+struct V3Lane {
+	u32 svc, job;
+	u32 pos, ls, lq, ll, paired;
+	u32 cand_p, cand2, len1;
+	u32 sumq, sumr;
+	const u64 *q_code;
+	u32 qlen, c_end;
+	u64 unit;
+	u32 b_pos, b_ls, b_lq, b_ll, b_paired, a_true, flag;
+};
+
+// One trip of a running lane (L.svc == V3_RUN). `col` = this lane's column of the count cells
+// (cell x at col[x * V3_CELL_STRIDE]).
+template <int PHASE>
+V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col) {
+	const u32 t = c.t;
+	u32 sign = 1u;
+	if (L.job == V3_STEP) {
+		if (PHASE == 1) {
+			if (L.pos >= L.c_end) {
+				L.svc = V3_SVC_FINISH;
+				return;
+			}
+		} else {
+			// the two chains inside chunk c+1 (L.c_end = its end): stop when they are in the same
+			// state, give up when either leaves the chunk, else advance the one that is behind
+			bool same = L.pos == L.b_pos && L.ls == L.b_ls && L.lq == L.b_lq && L.ll == L.b_ll && L.paired == L.b_paired;
+			u32 t_pos = L.a_true ? L.pos : L.b_pos, p_pos = L.a_true ? L.b_pos : L.pos;
+			if (same || t_pos >= L.c_end || p_pos >= L.c_end) {
+				L.flag = same ? 1u : 0u;
+				L.svc = V3_SVC_FINISH;
+				return;
+			}
+			bool step_true = t_pos <= p_pos;
+			if (step_true != (L.a_true != 0u)) {
+				u32 x;
+				x = L.pos, L.pos = L.b_pos, L.b_pos = x;
+				x = L.ls, L.ls = L.b_ls, L.b_ls = x;
+				x = L.lq, L.lq = L.b_lq, L.b_lq = x;
+				x = L.ll, L.ll = L.b_ll, L.b_ll = x;
+				x = L.paired, L.paired = L.b_paired, L.b_paired = x;
+				L.a_true ^= 1u;
+			}
+		}
+	}
+	if (PHASE == 2) sign = L.a_true ? 1u : 0xffffffffu;
+
+	const u32 end_q = L.lq + L.ll, end_s = L.ls + L.ll;
+	const bool is_step = L.job == V3_STEP, is_ext = L.job == V3_EXT, is_cand = L.job >= V3_CAND;
+	const u32 g = L.pos - end_q;	 // process.c:88-89, gap = advance - last.length (pos_Q is fixed while a step lasts)
+	const u32 guess = end_s + g;	 // process.c:91: last.pos_S + advance
+	const bool lucky = is_step && g <= t && guess < c.N;
+	// a directory candidate on the diagonal of the last anchor and close behind it would pair with
+	// it (process.c:167-169): compare it through a window that starts at the end of the last anchor,
+	// like a lucky attempt, so that its gap columns are at hand
+	const bool diag = is_cand && g <= V3_MAX_T && L.cand_p - end_s == g;
+	const bool from_end = is_ext || lucky || diag;
+	// COLS: the gap columns of an anchor that paired over more than V3_MAX_T columns, V3_MAX_T per
+	// trip; they end where the anchor (already the "last" one) begins, L.len1 of them are left
+	const bool is_cols = L.job == V3_COLS;
+	const u32 wq = from_end ? end_q : (is_cols ? L.lq - L.len1 : L.pos);
+	const u32 ws = from_end ? end_s : (is_cols ? L.ls - L.len1 : (is_cand ? L.cand_p : 0u));
+	const u32 gg = (lucky || diag) ? g : 0u;  // columns of the window in front of the compare
+	const u32 cq = wq + gg, cs = ws + gg;
+	const u32 run = cs < c.mid ? c.mid - cs : (cs == c.mid ? 0u : c.N - cs);
+	const u32 rem = L.qlen - cq;
+	const u32 clim = (is_step && !lucky) ? 0u : (rem < run ? rem : run);
+
+	u64 q0, q1, s0, s1;
+	v3_window64(L.q_code, wq, q0, q1);
+	v3_window64(c.s_code, ws, s0, s1);
+	const u64 x0 = q0 ^ s0, x1 = q1 ^ s1;
+	const u64 m0 = (x0 | (x0 >> 1)) & V3_EVEN, m1 = (x1 | (x1 >> 1)) & V3_EVEN;
+	const u64 m0c = (m0 >> (2u * gg)) << (2u * gg);	 // gg <= V3_MAX_T
+	const u32 D = m0c ? (v3_ctz64(m0c) >> 1) : (m1 ? 32u + (v3_ctz64(m1) >> 1) : 64u);
+	const u32 raw = D - gg;
+	const bool complete = D < 64u || raw >= clim;
+	u32 matched = raw < clim ? raw : clim;
+	V3_STAT(trips);
+
+	if (is_ext) {
+		V3_STAT(ext_trips);
+		L.ll += matched;
+		if (complete) L.pos = L.lq + L.ll + 1u, L.job = V3_STEP;
+		return;
+	}
+
+	u32 cur_s = 0;
+	bool in_window = true;	// the gap columns of a pairing anchor are the low columns of this window
+	if (is_cols) {
+	} else if (is_cand) {
+		V3_STAT(cand_trips);
+		cur_s = L.cand_p, in_window = diag;
+		if (L.job == V3_CAND1) {
+			// first of two suffixes that carry the k-mer: remember its length, compare the other one
+			if (!complete) {
+				V3_STAT(slow_long);
+				L.job = V3_STEP, L.svc = V3_SVC_SLOW;
+				return;
+			}
+			const u32 other = L.cand2;
+			L.cand2 = L.cand_p, L.cand_p = other, L.len1 = matched, L.job = V3_CAND2;
+			return;
+		}
+		if (L.job == V3_CAND2) {
+			if (!complete && L.len1 >= matched) {  // both longer than a window: repeats
+				V3_STAT(slow_long);
+				L.job = V3_STEP, L.svc = V3_SVC_SLOW;
+				return;
+			}
+			if (L.len1 == matched) {  // process.c:122: two suffixes carry the longest match, no anchor
+				L.pos += matched + 1u, L.job = V3_STEP;
+				V3_STAT(steps);
+				return;
+			}
+			if (L.len1 > matched) matched = L.len1, cur_s = L.cand2, in_window = false;
+		}
+		if (matched < t) {	// process.c:122: unique but too short
+			L.pos += matched + 1u, L.job = V3_STEP;
+			V3_STAT(steps);
+			return;
+		}
+	} else if (lucky && matched >= t) {
+		cur_s = guess, in_window = true;
+		V3_STAT(lucky_hits);
+	} else {
+		// process.c:117: the longest match anywhere in RS, through the directory view
+		if (c.K <= 0 || L.qlen - L.pos < (u32)c.K) {
+			V3_STAT(slow_tail);
+			L.svc = V3_SVC_SLOW;
+			return;
+		}
+		const u64 kw = gg ? ((q0 >> (2u * gg)) | (q1 << (64u - 2u * gg))) : q0;
+		const u64 fe = v3_ld_fdir(c.fdir + v3_kmer_key(kw, c.K));
+		const u32 tag = (u32)(fe >> 62);
+		V3_STAT(lookups);
+		if (tag == 0u) {  // absent k-mer: only the length matters (it is < K <= threshold)
+			L.pos += (u32)fe + 1u;
+			V3_STAT(steps);
+			V3_STAT(tag0);
+		} else if (tag == 1u) {
+			L.cand_p = (u32)fe, L.job = V3_CAND;
+		} else if (tag == 2u) {
+			// two suffixes, both text positions in the entry; the one that could pair goes last so
+			// that its window is the one at hand when the anchor is accounted
+			const u32 p1 = (u32)fe & 0x7fffffffu, p2 = (u32)(fe >> 31) & 0x7fffffffu;
+			const bool p1_diag = p1 - end_s == g;
+			L.cand_p = p1_diag ? p2 : p1, L.cand2 = p1_diag ? p1 : p2, L.job = V3_CAND1;
+		} else {
+			V3_STAT(slow_tag3);
+			L.svc = V3_SVC_SLOW;
+		}
+		return;
+	}
+
+	// ---- an anchor: process.c:160-196
+	const bool pairs = !is_cols && cur_s > end_s && (L.pos - end_q) == (cur_s - end_s) && ((cur_s < c.border) == (L.ls < c.border));
+	u32 ncols = g;	// gap columns to classify from this window
+	if (is_cols) {
+		V3_STAT(cols_trips);
+		ncols = L.len1 < V3_MAX_T ? L.len1 : V3_MAX_T;
+	} else {
+		V3_STAT(steps);
+		if (pairs || L.paired || L.ll >= 2u * t) {	// model.c:247-254 for the previous anchor
+			L.sumq += (L.ll >> 2) * sign;
+			L.sumr += (L.ll & 3u) * sign;
+		}
+	}
+	if ((pairs && in_window) || is_cols) {
+		// model.c:309-337 on columns [0, ncols) of the window (1 <= ncols <= V3_MAX_T here)
+		const u32 g = ncols;
+		if (g == 1u) {
+			col[((((u32)s0 & 3u) << 2) | ((u32)q0 & 3u)) * V3_CELL_STRIDE] += sign;
+		} else {
+			V3_STAT(wide_gaps);
+			const u64 vm = V3_EVEN & ((1ULL << (2u * g)) - 1ULL);
+			u64 neq = m0 & vm;
+			const u64 eq = vm & ~neq, lo = q0 & V3_EVEN, hi = (q0 >> 1) & V3_EVEN;
+			col[0 * V3_CELL_STRIDE] += v3_popc64(eq & ~hi & ~lo) * sign;
+			col[5 * V3_CELL_STRIDE] += v3_popc64(eq & ~hi & lo) * sign;
+			col[10 * V3_CELL_STRIDE] += v3_popc64(eq & hi & ~lo) * sign;
+			col[15 * V3_CELL_STRIDE] += v3_popc64(eq & hi & lo) * sign;
+			while (neq) {
+				const u32 b = v3_ctz64(neq);
+				neq &= neq - 1ULL;
+				col[((((u32)(s0 >> b) & 3u) << 2) | ((u32)(q0 >> b) & 3u)) * V3_CELL_STRIDE] += sign;
+			}
+		}
+	}
+	if (is_cols) {
+		L.len1 -= ncols;
+		if (L.len1 == 0u) L.job = L.cand2 ? V3_EXT : V3_STEP;
+		return;
+	}
+	L.ls = cur_s, L.lq = L.pos, L.ll = matched, L.paired = pairs ? 1u : 0u;
+	if (complete) L.pos += matched + 1u;
+	L.job = complete ? V3_STEP : V3_EXT;
+	if (pairs && !in_window) {
+		// more than V3_MAX_T gap columns (or a window that does not hold them): classify them in
+		// COLS trips before the walk goes on; L.cand2 remembers whether the anchor still grows
+		V3_STAT(wide_pairs);
+		L.len1 = g, L.cand2 = complete ? 0u : 1u, L.job = V3_COLS;
+	}
+}
+
+// Unit number -> (query index k, chunk c). PHASE 2 units are the boundaries: unit (k, c) replays
+// the entry into chunk c + 1.
+V3_FN void v3_split_unit(u64 unit, u64 total, u32 cpq, u32 &k, u32 &c) {
+	if (total <= 0xffffffffULL) {
+		k = (u32)unit / cpq, c = (u32)unit - k * cpq;
+	} else {
+		k = (u32)(unit / cpq), c = (u32)(unit % cpq);
+	}
+}
+
+// Start unit (qid's planes at q_code, length qlen, chunk c). Returns false when the unit holds no work.
+// PHASE 1: records of a last chunk also get D = 0, flag = 1 here (nothing follows it).
+template <int PHASE>
+V3_FN bool v3_begin_unit(V3Lane &L, const V3Const &c, const u64 *q_code, u32 qlen, u32 chunk_no, u32 *rec, u32 *col) {
+	const u64 start = (u64)chunk_no * c.chunk;
+	if (start >= qlen) return false;
+	const u64 end1 = start + c.chunk, end2 = start + 2ULL * c.chunk;
+	const u32 c_end = (u32)(end1 < qlen ? end1 : qlen);
+	if (PHASE == 2 && c_end >= qlen) return false;	// last chunk: no boundary
+	L.q_code = q_code, L.qlen = qlen;
+	L.job = V3_STEP, L.cand_p = 0, L.cand2 = 0, L.len1 = 0, L.sumq = 0, L.sumr = 0, L.flag = 1;
+#pragma unroll
+	for (int x = 0; x < 16; x++) col[x * V3_CELL_STRIDE] = 0;
+	if (PHASE == 1) {
+		L.pos = (u32)start, L.ls = L.lq = L.ll = L.paired = 0;
+		L.c_end = c_end;
+		if (c_end >= qlen) {
+#pragma unroll
+			for (int x = 0; x < 16; x++) rec[16 + x] = 0;
+			rec[37] = 1;
+		}
+	} else {
+		// chain A = the true chain leaving chunk c (E_c, written by the PHASE 1 launch), chain B =
+		// the amnesic walk of chunk c + 1
+		L.pos = rec[32], L.ls = rec[33], L.lq = rec[34], L.ll = rec[35], L.paired = rec[36];
+		L.b_pos = c_end, L.b_ls = L.b_lq = L.b_ll = L.b_paired = 0;
+		L.a_true = 1;
+		L.c_end = (u32)(end2 < qlen ? end2 : qlen);
+	}
+	return true;
+}
+
+// Write what this launch owes the record of the finished unit.
+template <int PHASE>
+V3_FN void v3_finish_unit(const V3Lane &L, u32 *rec, const u32 *col) {
+	const u32 base = PHASE == 1 ? 0u : 16u;
+	const bool keep = PHASE == 1 || L.flag != 0u;  // a boundary that did not synchronise contributes nothing
+#pragma unroll
+	for (int x = 0; x < 16; x++) {
+		u32 v = col[x * V3_CELL_STRIDE];
+		if (x == 0 || x == 5 || x == 10 || x == 15) v += L.sumq;
+		if (x == 15) v += L.sumr;
+		rec[base + x] = keep ? v : 0u;
+	}
+	if (PHASE == 1) {
+		rec[32] = L.pos, rec[33] = L.ls, rec[34] = L.lq, rec[35] = L.ll, rec[36] = L.paired;
+	} else {
+		rec[37] = L.flag;
+	}
+}
+
+// Serve one parked lane. Env supplies what differs between the kernel and the emulation:
+//   u64 total; u32 *records; u64 next_unit(); bool open_unit(u64 unit, V3Lane &, u32 *&rec)  (query lookup +
+//   v3_begin_unit; false = no work in this unit); void slow_step(V3Lane &, u32 *col, u32 sign).
+template <int PHASE, class Env>
+V3_FN void v3_service(V3Lane &L, const V3Const &c, Env &env, u32 *col) {
+	if (L.svc == V3_SVC_SLOW) {
+		env.slow_step(L, col, (PHASE == 2 && !L.a_true) ? 0xffffffffu : 1u);
+		L.svc = V3_RUN;
+		return;
+	}
+	if (L.svc == V3_SVC_FINISH) {
+		v3_finish_unit<PHASE>(L, env.records + L.unit * ANDI_UNIT_WORDS, col);
+		L.svc = V3_SVC_FETCH;
+	}
+	if (L.svc == V3_SVC_FETCH) {
+		L.svc = V3_SVC_DONE;
+		for (;;) {
+			const u64 unit = env.next_unit();
+			if (unit >= env.total) break;
+			if (env.template open_unit<PHASE>(unit, L, c, col)) {
+				L.unit = unit, L.svc = V3_RUN;
+				break;
+			}
+		}
+	}
+}
+
+// When does a warp stop to serve its parked lanes? `parked` = lanes with a request, `running` =
+// lanes with a window job.
+V3_FN bool v3_serve_now(u32 parked, u32 running, u32 trip) {
+	return parked != 0u && (running == 0u || parked >= V3_SERVE_BATCH || (trip & (V3_SERVE_EVERY - 1u)) == V3_SERVE_EVERY - 1u);
+}

@@ -1,9 +1,9 @@
-"""Round-2 groundwork: the phase-binned walk kernel (andi_b200/csrc/experimental/) is not part of
-the library yet, but its per-unit phase logic is already checked here on the CPU. The phases
-header compiles both into the CUDA kernel and into a serial host emulation (emu_binned.cpp);
-this test builds the index with numpy from the oracle's suffix array, runs the emulation (same
-queues, same super-steps, one unit at a time), reduces its records the way k_walk_reduce does
-and compares with the oracle. Test infrastructure only; nothing here touches a GPU."""
+"""The round-2 walk kernels (andi_b200/csrc/walk_v3.cuh) on the CPU: their per-lane logic
+(walk_v3_lane.h) compiles both into the CUDA kernels and into a serial warp emulation
+(csrc/emu/emu_v3.cpp). This test builds the index with numpy from the oracle's suffix array, runs
+the emulation (32 lock-step lanes per warp, the kernel's service policy, PHASE 1 then PHASE 2),
+reduces its records the way k_walk_reduce does and compares with the oracle. Test infrastructure
+only; nothing here touches a GPU."""
 import ctypes as C
 import subprocess
 from pathlib import Path
@@ -15,25 +15,32 @@ import oracle
 from andi_b200 import synth
 
 ROOT = Path(__file__).resolve().parent.parent
-EXP = ROOT / "andi_b200" / "csrc" / "experimental"
+EMU = ROOT / "andi_b200" / "csrc" / "emu"
 UNIT_WORDS = 38
 CODE = np.full(256, 255, dtype=np.uint8)
 for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3), (b"#", 1)):
     CODE[ch[0]] = v
+STATS = ["trips", "ext_trips", "cand_trips", "steps", "lucky_hits", "lookups", "tag0", "wide_gaps", "slow_steps", "slow_tail", "slow_tag3", "wide_pairs", "slow_long", "cols_trips",
+         "warp_trips", "running_lanes", "services", "served_lanes"]
+
+
+def load_emu():
+    so = EMU / "libemu_v3.so"
+    src = [EMU / "emu_v3.cpp", EMU.parent / "walk_v3_lane.h"]
+    if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src[0])], check=True,
+                       cwd=EMU, capture_output=True)
+    L = C.CDLL(str(so))
+    L.emu_walk_v3.restype = C.c_long
+    L.emu_walk_v3.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    assert L.emu_v3_stats() == len(STATS)
+    return L
 
 
 @pytest.fixture(scope="module")
 def emu():
-    so = EXP / "libemu_binned.so"
-    src = [EXP / "emu_binned.cpp", EXP / "walk_binned_phases.h"]
-    if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
-        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src[0])], check=True,
-                       cwd=EXP, capture_output=True)
-    L = C.CDLL(str(so))
-    L.emu_walk_binned.restype = C.c_long
-    L.emu_walk_binned.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
-                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
-    return L
+    return load_emu()
 
 
 def pack(text: bytes) -> np.ndarray:
@@ -49,7 +56,8 @@ def pack(text: bytes) -> np.ndarray:
 
 def directory_view(rs: bytes, SA: np.ndarray, K: int) -> np.ndarray:
     """fdir of sa_bucket.cuh / esa_kernels.cuh, restated with numpy: per k-mer tag 0 + longest
-    present prefix / tag 1 + text position of its only suffix / tag 2 + first SA index, count."""
+    present prefix / tag 1 + text position of its only suffix / tag 2 + the text positions of its two suffixes
+    (31 bits each) / tag 3 + first SA index, count."""
     N, mid = len(rs), len(rs) // 2
     codes = CODE[np.frombuffer(rs, dtype=np.uint8)].astype(np.int64)
     pos = np.arange(N)
@@ -81,8 +89,10 @@ def directory_view(rs: bytes, SA: np.ndarray, K: int) -> np.ndarray:
     fdir = np.where(count == 0, plen, 0).astype(np.uint64)
     one = count == 1
     fdir[one] = (np.uint64(1) << np.uint64(62)) | SA[first[one]].astype(np.uint64)
-    many = count > 1
-    fdir[many] = (np.uint64(2) << np.uint64(62)) | (count[many].astype(np.uint64) << np.uint64(32)) | first[many].astype(np.uint64)
+    two = count == 2
+    fdir[two] = (np.uint64(2) << np.uint64(62)) | (SA[first[two] + 1].astype(np.uint64) << np.uint64(31)) | SA[first[two]].astype(np.uint64)
+    many = count > 2
+    fdir[many] = (np.uint64(3) << np.uint64(62)) | (count[many].astype(np.uint64) << np.uint64(32)) | first[many].astype(np.uint64)
     return fdir
 
 
@@ -108,22 +118,16 @@ def reduce_records(rec: np.ndarray, qlens, chunk: int, cpq: int, threshold: int,
     return out
 
 
-# (repeat-rich texts and anchors longer than a chunk leave chunk boundaries unsynchronised; that path belongs to k_walk_reduce,
-# not to the kernel emulated here, so those sets run with one chunk per query)
-@pytest.mark.parametrize("name,chunk", [("subst", 1000), ("subst", 4096), ("indel", 700), ("repeat", 1 << 20),
-                                        ("identical", 1 << 20), ("lowent", 1 << 20), ("short", 1 << 20), ("unrelated", 1 << 20),
-                                        ("revcomp", 2048)])
-@pytest.mark.parametrize("seed", [0, 12345])  # 0: the kernel's lock-step super-steps; else: a random asynchronous order
-def test_binned_phases_match_the_oracle(emu, name, chunk, seed):
-    from conftest import stress_sequences
 
-    seqs = [s for s in stress_sequences()[name] if b"!" not in s]
-    want = oracle.rows(seqs, "JC")
+def emulate_rows(emu, seqs, chunk, warps=3, stats=None):
+    """All rows of the matrix through the emulation; returns (rows, per-phase statistics)."""
     qplanes = [pack(s) for s in seqs]
     q_off = np.cumsum([0] + [len(p) for p in qplanes[:-1]]).astype(np.uint64)
     pool = np.concatenate(qplanes)
     q_len = np.array([len(s) for s in seqs], dtype=np.uint32)
     cpq = max(1, -(-int(q_len.max()) // chunk))
+    rows = np.zeros((len(seqs), len(seqs), 17), dtype=np.uint32)
+    total = np.zeros(2 * len(STATS), dtype=np.uint64)
     for i, subject in enumerate(seqs):
         o = oracle.OracleEsa(subject)
         rs, SA = o.rs, o.array("SA").astype(np.uint32)
@@ -132,10 +136,27 @@ def test_binned_phases_match_the_oracle(emu, name, chunk, seed):
         K = min(t, max(4, round(np.log(N) / np.log(4))))
         s_code, fdir = pack(rs), directory_view(rs, SA, K)
         rec = np.zeros((len(seqs) * cpq, UNIT_WORDS), dtype=np.uint32)
-        stats = np.zeros(14, dtype=np.uint64)
-        steps = emu.emu_walk_binned(s_code.ctypes.data, N, N // 2, SA.ctypes.data, fdir.ctypes.data, K, i, t, pool.ctypes.data,
-                                    q_off.ctypes.data, q_len.ctypes.data, len(seqs), chunk, cpq, rec.ctypes.data, stats.ctypes.data, seed)
-        assert steps > 0
-        got = reduce_records(rec, [int(x) for x in q_len], chunk, cpq, t, skip=i)
-        assert np.array_equal(got, want[i]), (name, i, chunk, seed, stats.tolist())
+        st = np.zeros(2 * len(STATS), dtype=np.uint64)
+        rc = emu.emu_walk_v3(s_code.ctypes.data, N, N // 2, SA.ctypes.data, fdir.ctypes.data, K, i, t, pool.ctypes.data,
+                             q_off.ctypes.data, q_len.ctypes.data, len(seqs), chunk, cpq, rec.ctypes.data, st.ctypes.data, warps)
+        assert rc == 0
+        total += st
+        rows[i] = reduce_records(rec, [int(x) for x in q_len], chunk, cpq, t, skip=i)
         o.close()
+    n = len(STATS)
+    return rows, {"phase1": dict(zip(STATS, total[:n].tolist())), "phase2": dict(zip(STATS, total[n:].tolist()))}
+
+
+# (repeat-rich texts and anchors longer than a chunk leave chunk boundaries unsynchronised; that path belongs to k_walk_reduce,
+# not to the kernels emulated here, so those sets run with one chunk per query)
+@pytest.mark.parametrize("name,chunk", [("subst", 1000), ("subst", 4096), ("indel", 700), ("repeat", 1 << 20),
+                                        ("identical", 1 << 20), ("lowent", 1 << 20), ("short", 1 << 20), ("unrelated", 1 << 20),
+                                        ("revcomp", 2048)])
+@pytest.mark.parametrize("warps", [1, 5])
+def test_v3_lane_logic_matches_the_oracle(emu, name, chunk, warps):
+    from conftest import stress_sequences
+
+    seqs = [s for s in stress_sequences()[name] if b"!" not in s]
+    want = oracle.rows(seqs, "JC")
+    got, stats = emulate_rows(emu, seqs, chunk, warps)
+    assert np.array_equal(got, want), (name, chunk, warps, stats)
