@@ -675,5 +675,8 @@ extern "C" int andi_esa_get_match(const andi_esa *E, const char *const *queries,
 // ------------------------------------------------------------------ the walk (host side)
 #include "walk_host.cuh"
 
+// ------------------------------------------------------------------ several GPUs
+#include "multi_host.cuh"
+
 // ------------------------------------------------------------------ part B: reference symbols
 #include "compat.cuh"

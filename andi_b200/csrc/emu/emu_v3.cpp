@@ -21,8 +21,9 @@ typedef uint32_t u32;
 #define V3_CELL_STRIDE 1
 #define V3_SERVE_BATCH 6u
 #define V3_SERVE_EVERY 8u
+#define V3_COUNT_STATS 1
 
-enum { ST_trips, ST_ext_trips, ST_cand_trips, ST_steps, ST_lucky_hits, ST_lookups, ST_tag0, ST_wide_gaps, ST_slow_steps, ST_slow_tail, ST_slow_tag3, ST_wide_pairs, ST_slow_long, ST_cols_trips,
+enum { ST_trips, ST_ext_trips, ST_cand_trips, ST_steps, ST_lucky_hits, ST_lookups, ST_tag0, ST_wide_gaps, ST_slow_steps, ST_slow_tail, ST_slow_tag3, ST_wide_pairs, ST_slow_long, ST_cols_trips, ST_pushes, ST_drained, ST_drains, ST_drain_rounds,
 	   ST_warp_trips, ST_running_lanes, ST_services, ST_served_lanes, ST_N };
 static u64 *g_stats = nullptr;
 #define V3_STAT(name)                \
@@ -31,7 +32,8 @@ static u64 *g_stats = nullptr;
 	} while (0)
 
 static inline u32 v3_ctz64(u64 x) { return (u32)__builtin_ctzll(x); }
-static inline u32 v3_popc64(u64 x) { return (u32)__builtin_popcountll(x); }
+static inline u32 v3_ctz32(u32 x) { return x ? (u32)__builtin_ctz(x) : 32u; }
+static inline u32 v3_popc32(u32 x) { return (u32)__builtin_popcount(x); }
 static inline u64 v3_ld_fdir(const u64 *p) { return *p; }
 static inline void v3_window64(const u64 *w, u32 pos, u64 &lo, u64 &hi) {
 	u32 i = pos >> 5, sh = (pos & 31u) * 2u;
@@ -144,6 +146,9 @@ static void run_phase(Env &env, const V3Const &c, u32 n_warps) {
 	struct Warp {
 		V3Lane lane[32];
 		u32 cells[32][16];
+		u32 pq[32][V3_PEND_SLOTS], ps[32][V3_PEND_SLOTS];
+		unsigned char pg[32][V3_PEND_SLOTS];
+		V3Pend pend(u32 x) { return V3Pend{pq[x], ps[x], pg[x]}; }
 		u32 trip = 0;
 		bool done = false;
 	};
@@ -165,11 +170,17 @@ static void run_phase(Env &env, const V3Const &c, u32 n_warps) {
 			if (v3_serve_now(parked, running, w.trip)) {
 				if (g_stats) g_stats[ST_services]++, g_stats[ST_served_lanes] += parked;
 				for (u32 x = 0; x < 32; x++)
-					if (w.lane[x].svc != V3_RUN && w.lane[x].svc != V3_SVC_DONE) v3_service<PHASE>(w.lane[x], c, env, w.cells[x]);
+					if (w.lane[x].svc != V3_RUN && w.lane[x].svc != V3_SVC_DONE) v3_service<PHASE>(w.lane[x], c, env, w.cells[x], w.pend(x));
+			}
+			u32 most = 0;
+			for (auto &l : w.lane) most = l.npend > most ? l.npend : most;
+			if (most > V3_PEND_SLOTS - 2u) {  // a queue is nearly full: the whole warp classifies what it has queued
+				if (g_stats) g_stats[ST_drains]++, g_stats[ST_drain_rounds] += most;
+				for (u32 x = 0; x < 32; x++) v3_drain_lane(w.lane[x], w.pend(x), w.cells[x]);
 			}
 			running = 0;
 			for (u32 x = 0; x < 32; x++)
-				if (w.lane[x].svc == V3_RUN) running++, v3_trip<PHASE>(w.lane[x], c, w.cells[x]);
+				if (w.lane[x].svc == V3_RUN) running++, v3_trip<PHASE>(w.lane[x], c, w.cells[x], w.pend(x));
 			if (g_stats && running) g_stats[ST_warp_trips]++, g_stats[ST_running_lanes] += running;
 			w.trip++;
 		}

@@ -27,7 +27,8 @@
 	} while (0)
 
 V3_FN u32 v3_ctz64(u64 x) { return (u32)(__ffsll((long long)x) - 1); }
-V3_FN u32 v3_popc64(u64 x) { return (u32)__popcll(x); }
+V3_FN u32 v3_ctz32(u32 x) { return (u32)__clz((int)__brev(x)); }  // 32 for x == 0
+V3_FN u32 v3_popc32(u32 x) { return (u32)__popc(x); }
 V3_FN u64 v3_ld_fdir(const u64 *p) { return __ldg(p); }
 V3_FN void v3_window64(const u64 *__restrict__ w, u32 pos, u64 &lo, u64 &hi) { window64(w, pos, lo, hi); }
 V3_FN u32 v3_kmer_key(u64 win, int k) { return kmer_key(win, k); }
@@ -77,14 +78,17 @@ __global__ void __launch_bounds__(V3_THREADS, V3_BLOCKS_PER_SM)
 k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 nq, u32 chunk,
 		  u32 cpq, u32 threshold, u32 *__restrict__ records, unsigned long long *__restrict__ next_unit) {
 	__shared__ u32 cells[16][V3_THREADS];
+	__shared__ u32 pend_q[V3_PEND_SLOTS][V3_THREADS], pend_s[V3_PEND_SLOTS][V3_THREADS];
+	__shared__ unsigned char pend_g[V3_PEND_SLOTS][V3_THREADS];
 	u32 *col = &cells[0][threadIdx.x];
+	const V3Pend P = {&pend_q[0][threadIdx.x], &pend_s[0][threadIdx.x], &pend_g[0][threadIdx.x]};
 	V3Const c;
 	c.t = threshold, c.N = S.rs.len, c.mid = S.rs.mid, c.border = S.rs.len / 2, c.chunk = chunk, c.cpq = cpq, c.K = S.K;
 	c.s_code = S.rs.code, c.fdir = S.fdir;
 	V3Env env = {S, (u64)nq * cpq, records, next_unit, queries, query_ids, threshold};
 	V3Lane L;
 	L.svc = V3_SVC_FETCH, L.job = V3_STEP;
-	L.pos = L.ls = L.lq = L.ll = L.paired = L.cand_p = L.cand2 = L.len1 = L.sumq = L.sumr = 0;
+	L.pos = L.ls = L.lq = L.ll = L.paired = L.cand_p = L.cand2 = L.len1 = L.sumq = L.sumr = L.npend = 0;
 	L.q_code = nullptr, L.qlen = 0, L.c_end = 0, L.unit = 0;
 	L.b_pos = L.b_ls = L.b_lq = L.b_ll = L.b_paired = 0, L.a_true = 1, L.flag = 1;
 	for (u32 trip = 0;; trip++) {
@@ -92,10 +96,19 @@ k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32
 		const unsigned running = __ballot_sync(0xffffffffu, L.svc == V3_RUN);
 		if (!(parked | running)) break;
 		if (v3_serve_now((u32)__popc(parked), (u32)__popc(running), trip)) {
-			if (L.svc != V3_RUN && L.svc != V3_SVC_DONE) v3_service<PHASE>(L, c, env, col);
+			if (L.svc != V3_RUN && L.svc != V3_SVC_DONE) v3_service<PHASE>(L, c, env, col, P);
 			__syncwarp();
 		}
-		if (L.svc == V3_RUN) v3_trip<PHASE>(L, c, col);
+		if (__any_sync(0xffffffffu, L.npend > V3_PEND_SLOTS - 2u)) {
+			// a queue is nearly full: the whole warp classifies what it has queued
+			for (u32 k = 0; k < V3_PEND_SLOTS; k++) {
+				if (!__any_sync(0xffffffffu, k < L.npend)) break;
+				if (k < L.npend) v3_classify_entry(P, k, col);
+				__syncwarp();
+			}
+			L.npend = 0;
+		}
+		if (L.svc == V3_RUN) v3_trip<PHASE>(L, c, col, P);
 		__syncwarp();
 	}
 }

@@ -39,7 +39,8 @@ enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V
 enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND = 3, V3_CAND1 = 4, V3_CAND2 = 5 };
 
 #define V3_EVEN 0x5555555555555555ULL
-#define V3_MAX_T 31u  // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
+#define V3_MAX_T 31u	   // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
+#define V3_PEND_SLOTS 6u   // pending-gap queue entries per lane (16 columns each)
 
 struct V3Const {
 	u32 t, N, mid, border, chunk, cpq;
@@ -55,16 +56,69 @@ struct V3Lane {
 	u32 pos, ls, lq, ll, paired;
 	u32 cand_p, cand2, len1;
 	u32 sumq, sumr;
+	u32 npend;
 	const u64 *q_code;
 	u32 qlen, c_end;
 	u64 unit;
 	u32 b_pos, b_ls, b_lq, b_ll, b_paired, a_true, flag;
 };
 
+// This lane's column of the pending-gap queue (entry k at q[k * V3_CELL_STRIDE] etc.): gap columns
+// that src/model.c:309-337 has to classify, 16 per entry as 32-bit halves of the two windows.
+// Classifying them on the spot would run with the three or four lanes of a warp that happen to have
+// a wide gap in this trip (28 % of all warp instructions in the first form of this kernel); queued,
+// the whole warp classifies together once any lane's queue is nearly full (v3_drain).
+struct V3Pend {
+	u32 *q, *s;
+	unsigned char *g;  // number of columns (1..16) | 0x80 when the entry counts negatively (PHASE 2)
+};
+
+V3_FN void v3_push_gap(V3Lane &L, const V3Pend &P, u64 q0, u64 s0, u32 g, u32 sign) {
+	const u32 neg = sign == 1u ? 0u : 0x80u;
+	const u32 k = L.npend;
+	P.q[k * V3_CELL_STRIDE] = (u32)q0, P.s[k * V3_CELL_STRIDE] = (u32)s0;
+	P.g[k * V3_CELL_STRIDE] = (unsigned char)((g < 16u ? g : 16u) | neg);
+	if (g > 16u) {
+		P.q[(k + 1u) * V3_CELL_STRIDE] = (u32)(q0 >> 32), P.s[(k + 1u) * V3_CELL_STRIDE] = (u32)(s0 >> 32);
+		P.g[(k + 1u) * V3_CELL_STRIDE] = (unsigned char)((g - 16u) | neg);
+	}
+	L.npend = k + (g > 16u ? 2u : 1u);
+	V3_STAT(pushes);
+}
+
+// model.c:309-337 for queue entry k of this lane (the caller knows k < L.npend).
+V3_FN void v3_classify_entry(const V3Pend &P, u32 k, u32 *col) {
+	const u32 q = P.q[k * V3_CELL_STRIDE], s = P.s[k * V3_CELL_STRIDE], gb = P.g[k * V3_CELL_STRIDE];
+	const u32 g = gb & 0x7fu, sign = (gb & 0x80u) ? 0xffffffffu : 1u;
+	const u32 vm = g >= 16u ? 0x55555555u : (0x55555555u & ((1u << (2u * g)) - 1u));
+	const u32 x = q ^ s;
+	u32 neq = (x | (x >> 1)) & vm;
+	const u32 eq = vm & ~neq, ql = q & eq, qh = (q >> 1) & eq;
+	const u32 nt = v3_popc32(ql & qh), nc = v3_popc32(ql) - nt, ng = v3_popc32(qh) - nt, na = v3_popc32(eq) - nc - ng - nt;
+	col[0 * V3_CELL_STRIDE] += na * sign;
+	col[5 * V3_CELL_STRIDE] += nc * sign;
+	col[10 * V3_CELL_STRIDE] += ng * sign;
+	col[15 * V3_CELL_STRIDE] += nt * sign;
+	while (neq) {
+		const u32 b = v3_ctz32(neq);
+		neq &= neq - 1u;
+		col[((((s >> b) & 3u) << 2) | ((q >> b) & 3u)) * V3_CELL_STRIDE] += sign;
+	}
+	V3_STAT(drained);
+}
+
+// First differing column of a 64-column XOR window (64 when there is none), without branches.
+V3_FN u32 v3_first_diff(u64 x0, u64 x1) {
+	const u32 a = (u32)x0, b = (u32)(x0 >> 32), c = (u32)x1, d = (u32)(x1 >> 32);
+	// v3_ctz32(0) == 32: a piece without a difference contributes its 16 columns
+	const u32 da = v3_ctz32(a) >> 1, db = 16u + (v3_ctz32(b) >> 1), dc = 32u + (v3_ctz32(c) >> 1), dd = 48u + (v3_ctz32(d) >> 1);
+	return a ? da : (b ? db : (c ? dc : dd));
+}
+
 // One trip of a running lane (L.svc == V3_RUN). `col` = this lane's column of the count cells
-// (cell x at col[x * V3_CELL_STRIDE]).
+// (cell x at col[x * V3_CELL_STRIDE]). On entry L.npend <= V3_PEND_SLOTS - 2.
 template <int PHASE>
-V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col) {
+V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	const u32 t = c.t;
 	u32 sign = 1u;
 	if (L.job == V3_STEP) {
@@ -97,8 +151,9 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col) {
 	}
 	if (PHASE == 2) sign = L.a_true ? 1u : 0xffffffffu;
 
+	const u32 job = L.job;
 	const u32 end_q = L.lq + L.ll, end_s = L.ls + L.ll;
-	const bool is_step = L.job == V3_STEP, is_ext = L.job == V3_EXT, is_cand = L.job >= V3_CAND;
+	const bool is_step = job == V3_STEP, is_ext = job == V3_EXT, is_cols = job == V3_COLS, is_cand = job >= V3_CAND;
 	const u32 g = L.pos - end_q;	 // process.c:88-89, gap = advance - last.length (pos_Q is fixed while a step lasts)
 	const u32 guess = end_s + g;	 // process.c:91: last.pos_S + advance
 	const bool lucky = is_step && g <= t && guess < c.N;
@@ -107,9 +162,8 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col) {
 	// like a lucky attempt, so that its gap columns are at hand
 	const bool diag = is_cand && g <= V3_MAX_T && L.cand_p - end_s == g;
 	const bool from_end = is_ext || lucky || diag;
-	// COLS: the gap columns of an anchor that paired over more than V3_MAX_T columns, V3_MAX_T per
-	// trip; they end where the anchor (already the "last" one) begins, L.len1 of them are left
-	const bool is_cols = L.job == V3_COLS;
+	// COLS: the gap columns of an anchor that paired over more than V3_MAX_T columns, 16 per trip;
+	// they end where the anchor (already the "last" one) begins, L.len1 of them are left
 	const u32 wq = from_end ? end_q : (is_cols ? L.lq - L.len1 : L.pos);
 	const u32 ws = from_end ? end_s : (is_cols ? L.ls - L.len1 : (is_cand ? L.cand_p : 0u));
 	const u32 gg = (lucky || diag) ? g : 0u;  // columns of the window in front of the compare
@@ -121,138 +175,119 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col) {
 	u64 q0, q1, s0, s1;
 	v3_window64(L.q_code, wq, q0, q1);
 	v3_window64(c.s_code, ws, s0, s1);
-	const u64 x0 = q0 ^ s0, x1 = q1 ^ s1;
-	const u64 m0 = (x0 | (x0 >> 1)) & V3_EVEN, m1 = (x1 | (x1 >> 1)) & V3_EVEN;
-	const u64 m0c = (m0 >> (2u * gg)) << (2u * gg);	 // gg <= V3_MAX_T
-	const u32 D = m0c ? (v3_ctz64(m0c) >> 1) : (m1 ? 32u + (v3_ctz64(m1) >> 1) : 64u);
+	const u64 x0 = ((q0 ^ s0) >> (2u * gg)) << (2u * gg);  // gg <= V3_MAX_T
+	const u32 D = v3_first_diff(x0, q1 ^ s1);
 	const u32 raw = D - gg;
 	const bool complete = D < 64u || raw >= clim;
 	u32 matched = raw < clim ? raw : clim;
 	V3_STAT(trips);
 
-	if (is_ext) {
-		V3_STAT(ext_trips);
-		L.ll += matched;
-		if (complete) L.pos = L.lq + L.ll + 1u, L.job = V3_STEP;
-		return;
+	// ---- what the window decides. Deliberately written as selects, not as if-blocks: every branch
+	// region runs with the few lanes that need it while the rest of the warp waits (the first form
+	// of this kernel spent two thirds of its issue slots that way).
+	const bool c0 = job == V3_CAND, c1 = job == V3_CAND1, c2 = job == V3_CAND2;
+	const u32 l1 = L.len1;
+	// EXT: the anchor grows; done when the window saw its end
+	L.ll += is_ext ? matched : 0u;
+	const bool ext_done = is_ext && complete;
+	// CAND1 (first of two suffixes that carry the k-mer): remember its length, compare the other one.
+	// CAND2: the longer of the two is the match; equal lengths = not unique (process.c:122).
+	// A candidate longer than the window is fine when it is the only / the longer one (EXT follows).
+	const bool slow_long = (c1 && !complete) || (c2 && !complete && l1 >= matched);
+	const bool tie = c2 && l1 == matched, first_better = c2 && l1 > matched;
+	u32 cur_s = is_cand ? (first_better ? L.cand2 : L.cand_p) : guess;
+	const bool in_window = (lucky || diag) && !first_better;
+	matched = first_better ? l1 : matched;
+	const bool cand_final = (c0 || c2) && !slow_long;
+	const bool anchor = is_step ? (lucky && matched >= t) : (cand_final && !tie && matched >= t);
+	bool plain_end = cand_final && !anchor;	 // process.c:122: no anchor, pos_Q += length + 1
+	const bool lookup = is_step && !anchor;
+	{
+		const u32 p = L.cand_p;
+		L.cand_p = c1 ? L.cand2 : p, L.cand2 = c1 ? p : L.cand2, L.len1 = c1 ? matched : l1;
 	}
-
-	u32 cur_s = 0;
-	bool in_window = true;	// the gap columns of a pairing anchor are the low columns of this window
+	u32 next_job = c1 ? (u32)V3_CAND2 : (ext_done ? (u32)V3_STEP : job);
+	if (ext_done) L.pos = L.lq + L.ll + 1u;
+	if (slow_long) next_job = V3_STEP, L.svc = V3_SVC_SLOW;
+	L.job = next_job;
+	// what goes to the pending-gap queue at the end of this trip: COLS trips fetch the gap columns of
+	// an anchor that paired over more than V3_MAX_T columns, 16 per trip
+	u32 push_n = is_cols ? (l1 < 16u ? l1 : 16u) : 0u;
 	if (is_cols) {
-	} else if (is_cand) {
-		V3_STAT(cand_trips);
-		cur_s = L.cand_p, in_window = diag;
-		if (L.job == V3_CAND1) {
-			// first of two suffixes that carry the k-mer: remember its length, compare the other one
-			if (!complete) {
-				V3_STAT(slow_long);
-				L.job = V3_STEP, L.svc = V3_SVC_SLOW;
-				return;
-			}
-			const u32 other = L.cand2;
-			L.cand2 = L.cand_p, L.cand_p = other, L.len1 = matched, L.job = V3_CAND2;
-			return;
-		}
-		if (L.job == V3_CAND2) {
-			if (!complete && L.len1 >= matched) {  // both longer than a window: repeats
-				V3_STAT(slow_long);
-				L.job = V3_STEP, L.svc = V3_SVC_SLOW;
-				return;
-			}
-			if (L.len1 == matched) {  // process.c:122: two suffixes carry the longest match, no anchor
-				L.pos += matched + 1u, L.job = V3_STEP;
-				V3_STAT(steps);
-				return;
-			}
-			if (L.len1 > matched) matched = L.len1, cur_s = L.cand2, in_window = false;
-		}
-		if (matched < t) {	// process.c:122: unique but too short
-			L.pos += matched + 1u, L.job = V3_STEP;
-			V3_STAT(steps);
-			return;
-		}
-	} else if (lucky && matched >= t) {
-		cur_s = guess, in_window = true;
-		V3_STAT(lucky_hits);
-	} else {
+		L.len1 = l1 - push_n;
+		if (l1 == push_n) L.job = L.cand2 ? V3_EXT : V3_STEP;
+	}
+#ifdef V3_COUNT_STATS
+	if (is_ext) V3_STAT(ext_trips);
+	if (is_cols) V3_STAT(cols_trips);
+	if (is_cand) V3_STAT(cand_trips);
+	if (slow_long) V3_STAT(slow_long);
+#endif
+
+	if (lookup) {
 		// process.c:117: the longest match anywhere in RS, through the directory view
 		if (c.K <= 0 || L.qlen - L.pos < (u32)c.K) {
 			V3_STAT(slow_tail);
 			L.svc = V3_SVC_SLOW;
-			return;
-		}
-		const u64 kw = gg ? ((q0 >> (2u * gg)) | (q1 << (64u - 2u * gg))) : q0;
-		const u64 fe = v3_ld_fdir(c.fdir + v3_kmer_key(kw, c.K));
-		const u32 tag = (u32)(fe >> 62);
-		V3_STAT(lookups);
-		if (tag == 0u) {  // absent k-mer: only the length matters (it is < K <= threshold)
-			L.pos += (u32)fe + 1u;
-			V3_STAT(steps);
-			V3_STAT(tag0);
-		} else if (tag == 1u) {
-			L.cand_p = (u32)fe, L.job = V3_CAND;
-		} else if (tag == 2u) {
-			// two suffixes, both text positions in the entry; the one that could pair goes last so
-			// that its window is the one at hand when the anchor is accounted
+		} else {
+			const u64 kw = gg ? ((q0 >> (2u * gg)) | (q1 << (64u - 2u * gg))) : q0;
+			const u64 fe = v3_ld_fdir(c.fdir + v3_kmer_key(kw, c.K));
+			const u32 tag = (u32)(fe >> 62);
+			V3_STAT(lookups);
+			// tag 0, absent k-mer: only the length matters (it is < K <= threshold)
+			plain_end = tag == 0u, matched = (u32)fe;
+			if (tag == 0u) V3_STAT(tag0);
+			// tag 1: the only suffix; tag 2: two suffixes, both text positions in the entry -- the
+			// one that could pair goes last so that its window is the one at hand when the anchor
+			// is accounted
 			const u32 p1 = (u32)fe & 0x7fffffffu, p2 = (u32)(fe >> 31) & 0x7fffffffu;
 			const bool p1_diag = p1 - end_s == g;
-			L.cand_p = p1_diag ? p2 : p1, L.cand2 = p1_diag ? p1 : p2, L.job = V3_CAND1;
-		} else {
-			V3_STAT(slow_tag3);
-			L.svc = V3_SVC_SLOW;
+			if (tag == 1u) L.cand_p = (u32)fe, L.job = V3_CAND;
+			if (tag == 2u) L.cand_p = p1_diag ? p2 : p1, L.cand2 = p1_diag ? p1 : p2, L.job = V3_CAND1;
+			if (tag == 3u) {
+				V3_STAT(slow_tag3);
+				L.svc = V3_SVC_SLOW;
+			}
 		}
-		return;
 	}
-
-	// ---- an anchor: process.c:160-196
-	const bool pairs = !is_cols && cur_s > end_s && (L.pos - end_q) == (cur_s - end_s) && ((cur_s < c.border) == (L.ls < c.border));
-	u32 ncols = g;	// gap columns to classify from this window
-	if (is_cols) {
-		V3_STAT(cols_trips);
-		ncols = L.len1 < V3_MAX_T ? L.len1 : V3_MAX_T;
-	} else {
+	if (plain_end) {
 		V3_STAT(steps);
+		L.pos += matched + 1u, L.job = V3_STEP;
+	}
+	if (anchor) {
+		// ---- process.c:160-196
+		V3_STAT(steps);
+		if (is_step) V3_STAT(lucky_hits);
+		const bool pairs = cur_s > end_s && (L.pos - end_q) == (cur_s - end_s) && ((cur_s < c.border) == (L.ls < c.border));
 		if (pairs || L.paired || L.ll >= 2u * t) {	// model.c:247-254 for the previous anchor
 			L.sumq += (L.ll >> 2) * sign;
 			L.sumr += (L.ll & 3u) * sign;
 		}
-	}
-	if ((pairs && in_window) || is_cols) {
-		// model.c:309-337 on columns [0, ncols) of the window (1 <= ncols <= V3_MAX_T here)
-		const u32 g = ncols;
-		if (g == 1u) {
-			col[((((u32)s0 & 3u) << 2) | ((u32)q0 & 3u)) * V3_CELL_STRIDE] += sign;
-		} else {
-			V3_STAT(wide_gaps);
-			const u64 vm = V3_EVEN & ((1ULL << (2u * g)) - 1ULL);
-			u64 neq = m0 & vm;
-			const u64 eq = vm & ~neq, lo = q0 & V3_EVEN, hi = (q0 >> 1) & V3_EVEN;
-			col[0 * V3_CELL_STRIDE] += v3_popc64(eq & ~hi & ~lo) * sign;
-			col[5 * V3_CELL_STRIDE] += v3_popc64(eq & ~hi & lo) * sign;
-			col[10 * V3_CELL_STRIDE] += v3_popc64(eq & hi & ~lo) * sign;
-			col[15 * V3_CELL_STRIDE] += v3_popc64(eq & hi & lo) * sign;
-			while (neq) {
-				const u32 b = v3_ctz64(neq);
-				neq &= neq - 1ULL;
-				col[((((u32)(s0 >> b) & 3u) << 2) | ((u32)(q0 >> b) & 3u)) * V3_CELL_STRIDE] += sign;
+		L.ls = cur_s, L.lq = L.pos, L.ll = matched, L.paired = pairs ? 1u : 0u;
+		if (complete) L.pos += matched + 1u;
+		L.job = complete ? V3_STEP : V3_EXT;
+		if (pairs) {
+			// model.c:309-337 on the g gap columns (g >= 1)
+			if (!in_window) {
+				// more than V3_MAX_T of them, or a window that does not hold them: COLS trips fetch
+				// them before the walk goes on; L.cand2 remembers whether the anchor still grows
+				V3_STAT(wide_pairs);
+				L.len1 = g, L.cand2 = complete ? 0u : 1u, L.job = V3_COLS;
+			} else if (g == 1u) {
+				col[((((u32)s0 & 3u) << 2) | ((u32)q0 & 3u)) * V3_CELL_STRIDE] += sign;
+			} else {
+				V3_STAT(wide_gaps);
+				push_n = g;
 			}
 		}
 	}
-	if (is_cols) {
-		L.len1 -= ncols;
-		if (L.len1 == 0u) L.job = L.cand2 ? V3_EXT : V3_STEP;
-		return;
-	}
-	L.ls = cur_s, L.lq = L.pos, L.ll = matched, L.paired = pairs ? 1u : 0u;
-	if (complete) L.pos += matched + 1u;
-	L.job = complete ? V3_STEP : V3_EXT;
-	if (pairs && !in_window) {
-		// more than V3_MAX_T gap columns (or a window that does not hold them): classify them in
-		// COLS trips before the walk goes on; L.cand2 remembers whether the anchor still grows
-		V3_STAT(wide_pairs);
-		L.len1 = g, L.cand2 = complete ? 0u : 1u, L.job = V3_COLS;
-	}
+	if (push_n) v3_push_gap(L, P, q0, s0, push_n, sign);
+}
+
+// Classify everything this lane has queued.
+V3_FN void v3_drain_lane(V3Lane &L, const V3Pend &P, u32 *col) {
+	for (u32 k = 0; k < L.npend; k++) v3_classify_entry(P, k, col);
+	L.npend = 0;
 }
 
 // Unit number -> (query index k, chunk c). PHASE 2 units are the boundaries: unit (k, c) replays
@@ -275,7 +310,7 @@ V3_FN bool v3_begin_unit(V3Lane &L, const V3Const &c, const u64 *q_code, u32 qle
 	const u32 c_end = (u32)(end1 < qlen ? end1 : qlen);
 	if (PHASE == 2 && c_end >= qlen) return false;	// last chunk: no boundary
 	L.q_code = q_code, L.qlen = qlen;
-	L.job = V3_STEP, L.cand_p = 0, L.cand2 = 0, L.len1 = 0, L.sumq = 0, L.sumr = 0, L.flag = 1;
+	L.job = V3_STEP, L.cand_p = 0, L.cand2 = 0, L.len1 = 0, L.sumq = 0, L.sumr = 0, L.flag = 1, L.npend = 0;
 #pragma unroll
 	for (int x = 0; x < 16; x++) col[x * V3_CELL_STRIDE] = 0;
 	if (PHASE == 1) {
@@ -320,13 +355,14 @@ V3_FN void v3_finish_unit(const V3Lane &L, u32 *rec, const u32 *col) {
 //   u64 total; u32 *records; u64 next_unit(); bool open_unit(u64 unit, V3Lane &, u32 *&rec)  (query lookup +
 //   v3_begin_unit; false = no work in this unit); void slow_step(V3Lane &, u32 *col, u32 sign).
 template <int PHASE, class Env>
-V3_FN void v3_service(V3Lane &L, const V3Const &c, Env &env, u32 *col) {
+V3_FN void v3_service(V3Lane &L, const V3Const &c, Env &env, u32 *col, const V3Pend &P) {
 	if (L.svc == V3_SVC_SLOW) {
 		env.slow_step(L, col, (PHASE == 2 && !L.a_true) ? 0xffffffffu : 1u);
 		L.svc = V3_RUN;
 		return;
 	}
 	if (L.svc == V3_SVC_FINISH) {
+		v3_drain_lane(L, P, col);
 		v3_finish_unit<PHASE>(L, env.records + L.unit * ANDI_UNIT_WORDS, col);
 		L.svc = V3_SVC_FETCH;
 	}

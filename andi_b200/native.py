@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "andi_pool_size", "andi_pool_info", "andi_threshold", "andi_esa_build", "andi_esa_build_rs", "andi_esa_free",
     "andi_esa_len", "andi_esa_download", "andi_esa_get_match", "andi_dist_row", "andi_dist_anchor",
     "andi_dist_rows", "andi_dist_rows_device", "andi_get_stats", "andi_reset_stats",
+    "andi_pool_export", "andi_pool_import", "andi_dist_matrix_multi",
 ]
 
 
@@ -45,6 +46,7 @@ class Stats(C.Structure):
         ("esa_ms", C.c_double), ("walk_ms", C.c_double), ("total_ms", C.c_double),
         ("esa_launches", C.c_uint64), ("cub_calls", C.c_uint64), ("walk_launches", C.c_uint64), ("pairs", C.c_uint64),
         ("subjects", C.c_uint64), ("sa_rounds", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("p2p_bytes", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -166,15 +166,16 @@ def cpu_sample(host_seq, n_total, subjects, q_sample, model, threads):
     qids = [int(q) for q in rng.choice(n_total, size=min(q_sample, n_total - 1), replace=False) if q not in subjects]
     seqs = [host_seq(i) for i in subjects] + [host_seq(j) for j in qids]
     S = len(subjects)
+    ref_cells = None
     if oracle.ref_available():
-        _, t = oracle.ref_rows(seqs, model, s_begin=0, s_end=S, threads=threads)
+        ref_cells, t = oracle.ref_rows(seqs, model, s_begin=0, s_end=S, threads=threads)
         kind = "reference"
         esa_per_subject = t["esa_s"] / S
         walk_per_pair = t["walk_s"] / (S * (len(seqs) - 1))
         wall = t["wall_s"]
     else:
         t0 = time.perf_counter()
-        oracle.rows(seqs, model, s_begin=0, s_end=1)
+        ref_cells = oracle.rows(seqs, model, s_begin=0, s_end=1)
         wall = time.perf_counter() - t0
         kind, threads, S = "port", 1, 1
         esa_per_subject, walk_per_pair = 0.0, wall / (len(seqs) - 1)
@@ -185,6 +186,9 @@ def cpu_sample(host_seq, n_total, subjects, q_sample, model, threads):
                   f"esa_init {esa_per_subject:.3f} s/subject (SA by the oracle's divsufsort shim), "
                   f"dist_anchor {walk_per_pair * 1e3:.2f} ms/pair; extrapolated to rows of {n_total - 1} queries",
         "esa_s_per_subject": esa_per_subject, "walk_ms_per_pair": walk_per_pair * 1e3, "wall_s": wall,
+        # the checker's cells of this sample (popped before the line is printed): columns = `_ids`,
+        # rows = its first entries
+        "_cells": ref_cells, "_ids": list(subjects) + qids,
     }
 
 
@@ -215,6 +219,7 @@ def run_reference(args):
         cache.clear()
     value = float(np.mean([r["value"] for r in results]))
     last = results[-1]
+    last.pop("_cells", None), last.pop("_ids", None)
     last["value"] = value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -339,7 +344,6 @@ def main():
             "h2d_bytes_per_step": int(st2["h2d_bytes"] // args.steps), "d2h_bytes_per_step": int(st2["d2h_bytes"] // args.steps),
             "ms_per_step": ms2 / args.steps,
         }
-        # parity spot check of the timed output against the device-resident run of the same rows
         ctx2.close()
 
     # ---- roofline of the dominant kernel (the anchor walk)
@@ -368,7 +372,7 @@ def main():
     esa_mbp_s = st["subjects"] * ln / 1e6 / (st["esa_ms"] * 1e-3) if st["esa_ms"] > 0 else None
     esa_bytes = 14 * (2 * ln + 1) + 16.8e6
 
-    cpu = None
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         if host_pool is None:
             host_pool = chars.cpu()
@@ -380,6 +384,19 @@ def main():
         threads = os.cpu_count() or 1
         S = max(1, min(threads, g - 1))
         cpu = cpu_sample(host_seq, g, list(range(S)), args.cpu_queries, model, threads)
+        # ---- parity of the benched workload: the checker's cells of the sample against the cells
+        # the timed context computes for the same (subject, query) pairs of the full pool
+        ref_cells, ids = cpu.pop("_cells"), np.asarray(cpu.pop("_ids"))
+        rows_chk = ref_cells.shape[0]
+        chk = torch.empty((rows_chk, g, 17), dtype=torch.int32, device=device)
+        ctx.dist_rows_device(chk.data_ptr(), 0, rows_chk, 0.025, model)
+        torch.cuda.synchronize()
+        got = chk.cpu().numpy().view(np.uint32)[:, ids, :]
+        bad = np.argwhere((got != ref_cells).any(axis=2))
+        parity = {"cells": int(got.shape[0] * got.shape[1]), "mismatches": int(len(bad)), "against": cpu["kind"],
+                  "subjects": rows_chk, "queries_per_subject": int(len(ids))}
+        if len(bad):
+            parity["first_bad"] = [[int(ids[r]), int(ids[c])] for r, c in bad[:5]]
 
     if rank == 0:
         line = {
@@ -396,7 +413,7 @@ def main():
             "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(st["esa_launches"] + st["walk_launches"]),
             "cub_calls": int(st["cub_calls"]),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "esa_build": {"mbp_per_s": esa_mbp_s, "ms_per_subject": st["esa_ms"] / max(1, st["subjects"]),
                           "algorithmic_gbs": (esa_bytes * st["subjects"] / (st["esa_ms"] * 1e-3) / 1e9) if st["esa_ms"] > 0 else None,
                           "sa_rounds_per_subject": st["sa_rounds"] / max(1, st["subjects"])},
@@ -406,6 +423,8 @@ def main():
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity and parity["mismatches"]:
+        raise SystemExit(f"bench.py: the benched workload differs from the {parity['against']} in {parity['mismatches']} cells")
 
 
 if __name__ == "__main__":

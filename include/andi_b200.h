@@ -122,6 +122,41 @@ int andi_dist_rows(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, 
 int andi_dist_rows_device(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model,
 						  int low_memory, andi_model *d_out);
 
+/* ---- several GPUs (src/dist_hack.h:8,46-47: the reference spreads the subjects of distMatrix
+ * over THREADS OpenMP threads; here they are spread over devices).
+ *
+ * The packed pool of one context can be handed to another one without a second upload:
+ * andi_pool_export describes the planes of `ctx` (device pointers on ctx's device plus the
+ * host-side per-sequence facts); andi_pool_import copies them into `ctx` -- over NVLink /
+ * cudaMemcpyPeerAsync when `src_device` differs from ctx's device (pass the exporting context's
+ * device; -1 = "same device as ctx"). The view's pointers stay valid until the exporting
+ * context changes its pool. bench.py's ranks (one process per GPU) move the same planes with an
+ * NCCL broadcast and import them from their own device. */
+typedef struct andi_pool_view {
+	const void *d_code; /* 2-bit code plane, `words` u64 words */
+	const void *d_spec; /* separator plane, same geometry; all zero when any_separator == 0 */
+	size_t words;
+	size_t n;
+	const size_t *lens;		  /* n */
+	const double *gc;		  /* n */
+	const int *has_separator; /* n */
+	int any_separator;
+} andi_pool_view;
+int andi_pool_export(const andi_ctx *ctx, andi_pool_view *out);
+int andi_pool_import(andi_ctx *ctx, const andi_pool_view *view, int src_device);
+
+/* distMatrix / distMatrixLM (src/dist_hack.h:34-96) for the whole matrix on `n_devices` GPUs:
+ * one host thread per device, the pool uploaded and packed ONCE (on devices[0]) and copied
+ * packed to the others, subjects handed out in small batches from a shared queue (their cost
+ * varies with length and divergence), rows written straight into out[n * n]. `progress`
+ * (may be NULL) is called from the worker threads, serialised, after every batch with the
+ * number of (subject, query) pairs finished so far -- what src/dist_hack.h:37-43,74-95 prints.
+ * Returns ANDI_OK or the first failing device's error code; its message is copied to errbuf. */
+typedef void (*andi_progress_fn)(size_t pairs_done, size_t pairs_total, void *user);
+int andi_dist_matrix_multi(const int *devices, int n_devices, const char *const *seqs, const size_t *lens,
+						   size_t n, double p_value, int model, int low_memory, andi_model *out,
+						   andi_progress_fn progress, void *user, char *errbuf, size_t errbuf_len);
+
 /* Device-side timing of the last andi_dist_rows / andi_esa_build call on this context, taken
  * with CUDA events on the context's stream (milliseconds), plus launch counts. */
 typedef struct andi_stats {
@@ -135,6 +170,7 @@ typedef struct andi_stats {
 	uint64_t subjects;	/* indexes built */
 	uint64_t sa_rounds; /* prefix-doubling refinement rounds, summed over subjects */
 	uint64_t h2d_bytes, d2h_bytes;
+	uint64_t p2p_bytes; /* packed pool planes received from another device (andi_pool_import) */
 } andi_stats;
 int andi_get_stats(const andi_ctx *ctx, andi_stats *out);
 void andi_reset_stats(andi_ctx *ctx);
