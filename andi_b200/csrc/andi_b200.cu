@@ -148,6 +148,15 @@ static void harvest_events(andi_ctx *ctx) {
 	}
 }
 
+extern "C" int andi_device_count(void) {
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return count;
+}
+
 extern "C" int andi_ctx_create(int device, void *stream, andi_ctx **out) {
 	if (!out) return ANDI_ERR_ARG;
 	*out = nullptr;

@@ -104,14 +104,14 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	// PHASE 2 over all chunk boundaries; ANDI_B200_WALK=pipeline keeps the round-1 kernel
 	const bool v3 = quarter && !spec && v3_applies(S, threshold) && !(force && (strcmp(force, "basic") == 0 || strcmp(force, "pipeline") == 0));
 	int per_sm = 0;
+	const unsigned threads = v3 ? V3_THREADS : ANDI_WALK_THREADS;
 	if (v3)
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_v3<1>, ANDI_WALK_THREADS, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_v3<1>, V3_THREADS, 0));
 	else
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf, ANDI_WALK_THREADS, 0));
 	if (per_sm < 1) per_sm = 1;
 	unsigned long long units = (unsigned long long)nq * plan.cpq;
-	unsigned grid = (unsigned)std::min<unsigned long long>((units + ANDI_WALK_THREADS - 1) / ANDI_WALK_THREADS,
-															(unsigned long long)per_sm * ctx->sm_count);
+	unsigned grid = (unsigned)std::min<unsigned long long>((units + threads - 1) / threads, (unsigned long long)per_sm * ctx->sm_count);
 	cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
 	mark(ctx, e0);
 	if (!ctx->first_ev) {
@@ -121,10 +121,10 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	if (!ctx->walk_counter) CK(dalloc(ctx, &ctx->walk_counter, 2));
 	CK(cudaMemsetAsync(ctx->walk_counter, 0, 2 * sizeof(unsigned long long), ctx->stream));
 	if (v3) {
-		k_walk_v3<1><<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
+		k_walk_v3<1><<<grid, V3_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
 																   d_records, ctx->walk_counter);
 		if (plan.cpq > 1)
-			k_walk_v3<2><<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
+			k_walk_v3<2><<<grid, V3_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
 																	   d_records, ctx->walk_counter + 1);
 		ctx->st.walk_launches += plan.cpq > 1 ? 1 : 0;
 	} else {

@@ -11,7 +11,9 @@
 #include "walk_kernels.cuh"
 
 #define V3_FN __device__ __forceinline__
-#define V3_THREADS ANDI_WALK_THREADS
+#ifndef V3_THREADS
+#define V3_THREADS 256
+#endif
 #define V3_CELL_STRIDE V3_THREADS
 #ifndef V3_SERVE_BATCH
 #define V3_SERVE_BATCH 6u  // parked lanes that make a warp stop and serve them ...
@@ -35,6 +37,12 @@ V3_FN u32 v3_kmer_key(u64 win, int k) { return kmer_key(win, k); }
 
 #include "walk_v3_lane.h"
 
+struct V3Acc {	// the count cells of this lane, as walk_step<> wants them
+	u32 *col;
+	u32 sign;
+	__device__ __forceinline__ void add(u32 cell, u32 v) { col[cell * V3_CELL_STRIDE] += v * sign; }
+};
+
 // The generic step (walk_step of walk_kernels.cuh) for the few lanes the window jobs do not
 // cover; a real call, so its registers do not weigh on the main loop.
 __device__ __noinline__ void v3_slow_step(const SubjectIndex &S, u32 t, const u64 *q_code, u32 qlen, u32 *col, u32 sign,
@@ -43,7 +51,7 @@ __device__ __noinline__ void v3_slow_step(const SubjectIndex &S, u32 t, const u6
 	q.code = q_code, q.spec = nullptr, q.len = qlen, q.mid = 0xffffffffu;
 	WalkState w;
 	w.pos_q = pos, w.last_s = ls, w.last_q = lq, w.last_len = ll, w.paired = paired;
-	SharedAcc acc = {col, sign};
+	V3Acc acc = {col, sign};
 	walk_step<true, false>(S, q, t, w, acc);
 	pos = w.pos_q, ls = w.last_s, lq = w.last_q, ll = w.last_len, paired = w.paired;
 }

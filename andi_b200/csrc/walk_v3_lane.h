@@ -40,7 +40,9 @@ enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND = 3, V3_CAND1 = 4, V3
 
 #define V3_EVEN 0x5555555555555555ULL
 #define V3_MAX_T 31u	   // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
+#ifndef V3_PEND_SLOTS
 #define V3_PEND_SLOTS 6u   // pending-gap queue entries per lane (16 columns each)
+#endif
 
 struct V3Const {
 	u32 t, N, mid, border, chunk, cpq;
@@ -162,7 +164,7 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	// like a lucky attempt, so that its gap columns are at hand
 	const bool diag = is_cand && g <= V3_MAX_T && L.cand_p - end_s == g;
 	const bool from_end = is_ext || lucky || diag;
-	// COLS: the gap columns of an anchor that paired over more than V3_MAX_T columns, 16 per trip;
+	// COLS: the gap columns of an anchor that paired over more than V3_MAX_T columns, 32 per trip;
 	// they end where the anchor (already the "last" one) begins, L.len1 of them are left
 	const u32 wq = from_end ? end_q : (is_cols ? L.lq - L.len1 : L.pos);
 	const u32 ws = from_end ? end_s : (is_cols ? L.ls - L.len1 : (is_cand ? L.cand_p : 0u));
@@ -211,8 +213,8 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	if (slow_long) next_job = V3_STEP, L.svc = V3_SVC_SLOW;
 	L.job = next_job;
 	// what goes to the pending-gap queue at the end of this trip: COLS trips fetch the gap columns of
-	// an anchor that paired over more than V3_MAX_T columns, 16 per trip
-	u32 push_n = is_cols ? (l1 < 16u ? l1 : 16u) : 0u;
+	// an anchor that paired over more than V3_MAX_T columns, 32 per trip
+	u32 push_n = is_cols ? (l1 < 32u ? l1 : 32u) : 0u;
 	if (is_cols) {
 		L.len1 = l1 - push_n;
 		if (l1 == push_n) L.job = L.cand2 ? V3_EXT : V3_STEP;

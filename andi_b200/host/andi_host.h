@@ -39,7 +39,7 @@ typedef struct {
 	int model;				  /* ANDI_M_* */
 	double p_value;			  /* ANCHOR_P_VALUE, src/andi.c:48 */
 	unsigned long bootstrap;  /* number of extra matrices (b - 1), src/andi.c:198 */
-	unsigned long seed;		  /* 0 = time(NULL) like the reference */
+	unsigned long seed;		  /* --seed; without it the CLI seeds with time(NULL) like the reference */
 	int device;
 } host_config;
 
@@ -58,10 +58,12 @@ int fasta_read_join(const char *file_name, host_seqs *out, int *flags);
 andi_model model_average(const andi_model *a, const andi_model *b);
 double model_coverage(const andi_model *m);
 double model_estimate(const andi_model *m, int model_id);
-/* src/model.c:222-232 with an own MT19937 + multinomial (PARITY UNPINNED: no GSL here) */
+/* src/model.c:222-232 with an own MT19937 + multinomial from exact conditional binomials
+ * (PARITY UNPINNED: no GSL here, so the distribution is the reference's, the stream is not) */
 typedef struct host_rng host_rng;
 host_rng *host_rng_new(unsigned long seed);
 void host_rng_free(host_rng *r);
+uint32_t host_rng_binomial(host_rng *r, double p, uint32_t n); /* exact: inversion / BTPE */
 andi_model model_bootstrap(host_rng *r, andi_model datum);
 
 /* output.c : src/io.c:246-338 */

@@ -5,8 +5,10 @@
  *   -b/--bootstrap, -p, -l/--low-memory, -v, --file-of-filenames, --truncate-names,
  *   --progress, -h, --version.
  * calculate_distances (src/process.c:230-270) becomes: pack the pool on the GPU, one call to
- * andi_dist_rows, then the reference's host-side printing. Extra, not in the reference:
- * --seed N (bootstrap RNG; the reference seeds with time(NULL)), --device N. */
+ * andi_dist_matrix_multi (subjects spread over the GPUs named by --devices, as the reference spreads
+ * them over -t threads, src/dist_hack.h:8), then the reference's host-side printing. Extra, not in
+ * the reference: --seed N (bootstrap RNG; the reference seeds with time(NULL)), --device N,
+ * --devices LIST. */
 #define _GNU_SOURCE
 #include "andi_host.h"
 #include <err.h>
@@ -38,7 +40,8 @@ static void usage(int status) {
 		"  -h, --help           Display this help and exit\n"
 		"      --version        Output version information and acknowledgments\n"
 		"      --seed=INT       Seed of the bootstrap generator (default: time)\n"
-		"      --device=INT     CUDA device to use (default 0)\n";
+		"      --device=INT     CUDA device to use (default 0)\n"
+		"      --devices=LIST   CUDA devices to spread the subjects over, e.g. 0-7 or 0,2,3 or all\n";
 	fputs(text, status == EXIT_SUCCESS ? stdout : stderr);
 	exit(status);
 }
@@ -47,6 +50,44 @@ typedef struct {
 	char **data;
 	size_t size, capacity;
 } names;
+
+/* "0-7", "0,2,3", "1", "all" -> device numbers; returns how many (0 = malformed) */
+static int parse_devices(const char *arg, int *out, int cap) {
+	int n = 0;
+	if (!strcasecmp(arg, "all")) {
+		int count = andi_device_count();
+		for (int d = 0; d < count && n < cap; d++) out[n++] = d;
+		return n;
+	}
+	const char *p = arg;
+	while (*p) {
+		char *end;
+		long a = strtol(p, &end, 10), b;
+		if (end == p || a < 0) return 0;
+		b = a;
+		if (*end == '-') {
+			p = end + 1;
+			b = strtol(p, &end, 10);
+			if (end == p || b < a) return 0;
+		}
+		for (long d = a; d <= b && n < cap; d++) out[n++] = (int)d;
+		if (*end == ',') end++;
+		else if (*end) return 0;
+		p = end;
+	}
+	return n;
+}
+
+/* src/dist_hack.h:37-43,74-95: the progress line on stderr */
+typedef struct {
+	size_t n;
+} progress_state;
+
+static void print_progress(size_t done, size_t total, void *user) {
+	const progress_state *st = user;
+	fprintf(stderr, "\rComparing %zu sequences: %5.1f%% (%zu/%zu)", st->n, total ? 100.0 * (double)done / (double)total : 100.0, done,
+			total);
+}
 
 static void names_push(names *v, char *s) {
 	if (v->size == v->capacity) {
@@ -84,6 +125,7 @@ int main(int argc, char *argv[]) {
 												 {"progress", optional_argument, NULL, 0},
 												 {"seed", required_argument, NULL, 0},
 												 {"device", required_argument, NULL, 0},
+												 {"devices", required_argument, NULL, 0},
 												 {"help", no_argument, NULL, 'h'},
 												 {"verbose", no_argument, NULL, 'v'},
 												 {"join", no_argument, NULL, 'j'},
@@ -94,6 +136,8 @@ int main(int argc, char *argv[]) {
 												 {0, 0, 0, 0}};
 	host_config cfg = {.flags = 0, .model = ANDI_M_JC, .p_value = 0.025, .bootstrap = 0, .seed = 0, .device = 0};
 	names files = {0};
+	enum { P_AUTO, P_NEVER, P_ALWAYS } progress = P_AUTO; /* src/andi.c:83 */
+	int devices[64], n_devices = 0, seed_given = 0;
 
 	for (;;) {
 		int idx = 0;
@@ -110,12 +154,20 @@ int main(int argc, char *argv[]) {
 				} else if (!strcmp(name, "file-of-filenames")) {
 					read_file_of_filenames(optarg, &files, &cfg.flags);
 				} else if (!strcmp(name, "progress")) {
-					if (optarg && strcasecmp(optarg, "always") && strcasecmp(optarg, "auto") && strcasecmp(optarg, "never"))
+					/* src/andi.c:111-122 */
+					if (!optarg || !strcasecmp(optarg, "always")) progress = P_ALWAYS;
+					else if (!strcasecmp(optarg, "auto")) progress = P_AUTO;
+					else if (!strcasecmp(optarg, "never")) progress = P_NEVER;
+					else
 						warnx("invalid argument to --progress '%s'. Expected one of 'auto', 'always', or 'never'.", optarg);
 				} else if (!strcmp(name, "seed")) {
 					cfg.seed = strtoul(optarg, NULL, 10);
+					seed_given = 1;
 				} else if (!strcmp(name, "device")) {
 					cfg.device = atoi(optarg);
+				} else if (!strcmp(name, "devices")) {
+					n_devices = parse_devices(optarg, devices, 64);
+					if (!n_devices) errx(1, "Expected a list of CUDA devices for --devices (e.g. 0-7 or 0,2), but '%s' was given.", optarg);
 				}
 				break;
 			}
@@ -216,26 +268,33 @@ int main(int argc, char *argv[]) {
 			  "inaccurate distances. Try an alignment instead.");
 	}
 
-	/* ---- calculate_distances (src/process.c:230-270) on the GPU */
-	andi_ctx *ctx = NULL;
-	if (andi_ctx_create(cfg.device, NULL, &ctx)) errx(1, "No usable CUDA device: %s", andi_last_error(NULL));
+	/* src/andi.c:318-324 */
+	if (progress == P_AUTO) progress = isatty(STDERR_FILENO) ? P_ALWAYS : P_NEVER;
+	if (progress == P_ALWAYS) cfg.flags |= HF_PRINT_PROGRESS;
+
+	/* ---- calculate_distances (src/process.c:230-270) on the GPU(s) */
+	if (!n_devices) devices[0] = cfg.device, n_devices = 1;
 	const char **ptr = malloc(n * sizeof *ptr);
 	size_t *len = malloc(n * sizeof *len);
 	andi_model *M = malloc(n * n * sizeof *M);
 	if (!ptr || !len || !M)
 		err(errno, "Could not allocate enough memory for the comparison matrix. Try using --join or --low-memory.");
 	for (size_t i = 0; i < n; i++) ptr[i] = seqs.data[i].S, len[i] = seqs.data[i].len;
-	if (andi_pool_set_host(ctx, ptr, len, n)) errx(1, "%s", andi_last_error(ctx));
-	if (andi_dist_rows(ctx, 0, n, cfg.p_value, cfg.model, (cfg.flags & HF_LOW_MEMORY) != 0, M))
-		errx(1, "Failed to create index: %s", andi_last_error(ctx));
-	andi_ctx_destroy(ctx);
+	char msg[512];
+	progress_state pst = {n};
+	const int show = (cfg.flags & HF_PRINT_PROGRESS) != 0;
+	if (show) print_progress(0, n * n - n, &pst);
+	if (andi_dist_matrix_multi(devices, n_devices, ptr, len, n, cfg.p_value, cfg.model, (cfg.flags & HF_LOW_MEMORY) != 0, M,
+							   show ? print_progress : NULL, &pst, msg, sizeof msg))
+		errx(1, "Failed to create index: %s", msg);
+	if (show) fprintf(stderr, ", done.\n");
 
 	print_distances(stdout, M, &seqs, &cfg, 1, &cfg.flags);
 	if (cfg.flags & HF_VERBOSE) print_coverages(stdout, M, n);
 
 	if (cfg.bootstrap) {
 		/* src/process.c:289-321 */
-		host_rng *rng = host_rng_new(cfg.seed ? cfg.seed : (unsigned long)time(NULL));
+		host_rng *rng = host_rng_new(seed_given ? cfg.seed : (unsigned long)time(NULL));
 		andi_model *B = malloc(n * n * sizeof *B);
 		if (!rng || !B) err(errno, "Out of memory");
 		while (cfg.bootstrap--) {

@@ -88,8 +88,9 @@ double model_estimate(const andi_model *m, int model_id) {
 }
 
 /* ---- bootstrap: src/model.c:222-232 draws the 16 counts from a multinomial with GSL.
- * GSL is not available here, so this is MT19937 (Matsumoto & Nishimura) + conditional
- * binomials; distributionally equivalent, NOT stream-identical to GSL (parity unpinned). */
+ * GSL is not available here, so this is MT19937 (Matsumoto & Nishimura) + the conditional
+ * binomials gsl_ran_multinomial uses, each drawn EXACTLY (below); the same distribution as the
+ * reference's, NOT the same random stream as GSL's (parity unpinned). */
 struct host_rng {
 	uint32_t mt[624];
 	int at;
@@ -98,8 +99,7 @@ struct host_rng {
 host_rng *host_rng_new(unsigned long seed) {
 	host_rng *r = malloc(sizeof *r);
 	if (!r) return NULL;
-	if (seed == 0) seed = 4357;
-	r->mt[0] = (uint32_t)seed;
+	r->mt[0] = (uint32_t)seed; /* every seed is taken as given, 0 included (the CLI maps "no --seed" to the time) */
 	for (int i = 1; i < 624; i++) r->mt[i] = 1812433253u * (r->mt[i - 1] ^ (r->mt[i - 1] >> 30)) + (uint32_t)i;
 	r->at = 624;
 	return r;
@@ -125,33 +125,96 @@ static uint32_t rng_u32(host_rng *r) {
 
 static double rng_unit(host_rng *r) { return (rng_u32(r) + 0.5) / 4294967296.0; }
 
-static double rng_normal(host_rng *r) {
-	double u = rng_unit(r), v = rng_unit(r);
-	return sqrt(-2.0 * log(u)) * cos(6.283185307179586 * v);
+/* Binomial(n, p), EXACT (the reference draws through gsl_ran_binomial, src/model.c:229 via
+ * gsl_ran_multinomial): inversion by sequential search for small means, and for the rest the
+ * published BTPE algorithm (Kachitvichyanukul & Schmeiser, "Binomial random variate generation",
+ * CACM 31(2), 1988, steps 0-5.3): triangle / parallelogram / two exponential tails as the
+ * majorising function, squeeze, then the exact acceptance test. Same distribution as GSL, not
+ * the same random stream (parity with GSL unpinned). */
+static uint32_t binomial_inversion(host_rng *r, double p, uint32_t n) {
+	const double q = 1.0 - p, s = p / q, a = (n + 1.0) * s;
+	const double bound = fmin((double)n, n * p + 10.0 * sqrt(n * p * q + 1.0));
+	for (;;) {
+		double f = pow(q, (double)n), u = rng_unit(r);
+		uint32_t x = 0;
+		for (;;) {
+			if (u < f) return x;
+			if ((double)x > bound) break; /* numerical leftovers in the far tail: draw again */
+			u -= f;
+			x++;
+			f *= a / x - s;
+		}
+	}
 }
 
-/* Binomial(n, p): exact geometric-skip sampling for small n*p, otherwise a continuity-
- * corrected normal draw clamped to [0, n] (n*p*(1-p) is in the thousands for genome counts). */
-static uint32_t rng_binomial(host_rng *r, double p, uint32_t n) {
-	if (p <= 0.0 || n == 0) return 0;
-	if (p >= 1.0) return n;
-	int flip = p > 0.5;
-	double q = flip ? 1.0 - p : p;
-	uint32_t k;
-	if ((double)n * q < 64.0) {
-		double lq = log1p(-q), pos = 0.0;
-		k = 0;
-		for (;;) {
-			pos += floor(log(rng_unit(r)) / lq) + 1.0;
-			if (pos > (double)n) break;
-			k++;
+static double stirling_tail(double x) {
+	const double x2 = x * x;
+	return (13860.0 - (462.0 - (132.0 - (99.0 - 140.0 / x2) / x2) / x2) / x2) / x / 166320.0;
+}
+
+static uint32_t binomial_btpe(host_rng *r, double p, uint32_t nn) {
+	/* step 0: set-up (p <= 0.5, n*p >= 30) */
+	const double n = (double)nn, q = 1.0 - p, npq = n * p * q, fm = n * p + p;
+	const double m = floor(fm);
+	const double p1 = floor(2.195 * sqrt(npq) - 4.6 * q) + 0.5;
+	const double xm = m + 0.5, xl = xm - p1, xr = xm + p1;
+	const double c = 0.134 + 20.5 / (15.3 + m);
+	double a = (fm - xl) / (fm - xl * p);
+	const double laml = a * (1.0 + a / 2.0);
+	a = (xr - fm) / (xr * q);
+	const double lamr = a * (1.0 + a / 2.0);
+	const double p2 = p1 * (1.0 + 2.0 * c), p3 = p2 + c / laml, p4 = p3 + c / lamr;
+	for (;;) {
+		/* step 1: the triangle is accepted at once */
+		double u = rng_unit(r) * p4, v = rng_unit(r), y;
+		if (u <= p1) return (uint32_t)floor(xm - p1 * v + u);
+		if (u <= p2) { /* step 2: parallelograms */
+			const double x = xl + (u - p1) / c;
+			v = v * c + 1.0 - fabs(m - x + 0.5) / p1;
+			if (v > 1.0) continue;
+			y = floor(x);
+		} else if (u <= p3) { /* step 3: left exponential tail */
+			y = floor(xl + log(v) / laml);
+			if (y < 0.0) continue;
+			v = v * (u - p2) * laml;
+		} else { /* step 4: right exponential tail */
+			y = floor(xr - log(v) / lamr);
+			if (y > n) continue;
+			v = v * (u - p3) * lamr;
 		}
-	} else {
-		double x = floor((double)n * q + sqrt((double)n * q * (1.0 - q)) * rng_normal(r) + 0.5);
-		if (x < 0) x = 0;
-		if (x > (double)n) x = (double)n;
-		k = (uint32_t)x;
+		/* step 5: acceptance. 5.1: near the mode (or npq small) evaluate f(y)/f(m) by recursion */
+		const double k = fabs(y - m);
+		if (k <= 20.0 || k >= npq / 2.0 - 1.0) {
+			const double s = p / q, aa = s * (n + 1.0);
+			double f = 1.0;
+			if (m < y) {
+				for (double i = m + 1.0; i <= y; i += 1.0) f *= aa / i - s;
+			} else if (m > y) {
+				for (double i = y + 1.0; i <= m; i += 1.0) f /= aa / i - s;
+			}
+			if (v > f) continue;
+			return (uint32_t)y;
+		}
+		/* 5.2: squeezing on log f */
+		const double rho = (k / npq) * ((k * (k / 3.0 + 0.625) + 0.1666666666666) / npq + 0.5);
+		const double tt = -k * k / (2.0 * npq), lv = log(v);
+		if (lv < tt - rho) return (uint32_t)y;
+		if (lv > tt + rho) continue;
+		/* 5.3: the final test with Stirling's formula */
+		const double x1 = y + 1.0, f1 = m + 1.0, z = n + 1.0 - m, w = n - y + 1.0;
+		const double bound = xm * log(f1 / x1) + (n - m + 0.5) * log(z / w) + (y - m) * log(w * p / (x1 * q)) + stirling_tail(f1) +
+							 stirling_tail(z) + stirling_tail(x1) + stirling_tail(w);
+		if (lv > bound) continue;
+		return (uint32_t)y;
 	}
+}
+
+uint32_t host_rng_binomial(host_rng *r, double p, uint32_t n) {
+	if (!(p > 0.0) || n == 0) return 0;
+	if (p >= 1.0) return n;
+	const int flip = p > 0.5;
+	const double q = flip ? 1.0 - p : p;
+	const uint32_t k = (double)n * q < 30.0 ? binomial_inversion(r, q, n) : binomial_btpe(r, q, n);
 	return flip ? n - k : k;
 }
 
@@ -164,7 +227,7 @@ andi_model model_bootstrap(host_rng *r, andi_model datum) {
 		uint32_t draw = 0;
 		if (p[k] > 0.0 && left) {
 			double cond = p[k] / (norm - used_p);
-			draw = rng_binomial(r, cond > 1.0 ? 1.0 : cond, left);
+			draw = host_rng_binomial(r, cond > 1.0 ? 1.0 : cond, left);
 		}
 		datum.counts[k] = draw;
 		used_p += p[k];

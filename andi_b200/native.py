@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "andi_pool_size", "andi_pool_info", "andi_threshold", "andi_esa_build", "andi_esa_build_rs", "andi_esa_free",
     "andi_esa_len", "andi_esa_download", "andi_esa_get_match", "andi_dist_row", "andi_dist_anchor",
     "andi_dist_rows", "andi_dist_rows_device", "andi_get_stats", "andi_reset_stats",
-    "andi_pool_export", "andi_pool_import", "andi_dist_matrix_multi",
+    "andi_pool_export", "andi_pool_import", "andi_dist_matrix_multi", "andi_device_count",
 ]
 
 

@@ -60,6 +60,9 @@ enum {
 	ANDI_ESA_FULL = 1	 /* additionally CLD, FVC and the 4^10 prefix cache of src/esa.c:73-245,312-363 */
 };
 
+/* Number of usable CUDA devices (0 when there is none or the runtime fails). */
+int andi_device_count(void);
+
 /* Create a context on CUDA device `device`. `stream` is a cudaStream_t (e.g. torch's current
  * stream) or NULL for a private stream. */
 int andi_ctx_create(int device, void *stream, andi_ctx **out);
