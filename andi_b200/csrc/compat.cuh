@@ -7,7 +7,18 @@
 #include <mutex>
 #include <unordered_map>
 
-extern "C" int MODEL __attribute__((weak));	 // the reference's global (src/andi.c:50), if the host program has one
+// the reference's globals (src/global.h:20-48, defined in src/andi.c:45-50) and the host-side functions
+// calculate_distances hands its results to, if the host program has them
+extern "C" {
+extern int MODEL __attribute__((weak));
+extern int FLAGS __attribute__((weak));
+extern double ANCHOR_P_VALUE __attribute__((weak));
+extern long unsigned int BOOTSTRAP __attribute__((weak));
+void print_distances(const model *, const seq_t *, size_t, int) __attribute__((weak));
+void print_coverages(const model *, size_t) __attribute__((weak));
+model model_average(const model *, const model *) __attribute__((weak));
+model model_bootstrap(model) __attribute__((weak));
+}
 
 namespace {
 std::mutex g_compat_mutex;
@@ -130,4 +141,115 @@ extern "C" model dist_anchor(const esa_s *C, const char *query, size_t query_len
 	}
 	memcpy(&ret, &m, sizeof ret);
 	return ret;
+}
+
+// ------------------------------------------------------------------ the driver level
+// src/dist_hack.h:34-96 and src/process.c:230-321 as ONE batched GPU run.
+
+static int compat_devices(int *out, int cap) {
+	const char *list = getenv("ANDI_B200_DEVICES");
+	int n = 0;
+	if (list && *list) {
+		if (!strcmp(list, "all")) {
+			for (int d = 0, c = andi_device_count(); d < c && n < cap; d++) out[n++] = d;
+			return n;
+		}
+		const char *p = list;
+		while (*p && n < cap) {
+			char *end;
+			long a = strtol(p, &end, 10), b = a;
+			if (end == p || a < 0) break;
+			if (*end == '-') {
+				p = end + 1;
+				b = strtol(p, &end, 10);
+				if (end == p || b < a) break;
+			}
+			for (long d = a; d <= b && n < cap; d++) out[n++] = (int)d;
+			p = *end == ',' ? end + 1 : end;
+			if (*end && *end != ',') break;
+		}
+		if (n) return n;
+	}
+	const char *one = getenv("ANDI_B200_DEVICE");
+	out[0] = one ? atoi(one) : 0;
+	return 1;
+}
+
+static void compat_progress(size_t done, size_t total, void *user) {
+	// src/dist_hack.h:74-90
+	fprintf(stderr, "\rComparing %zu sequences: %5.1f%% (%zu/%zu)", *(const size_t *)user,
+			total ? 100.0 * (double)done / (double)total : 100.0, done, total);
+}
+
+static void compat_matrix(model *M, const seq_t *sequences, size_t n, int low_memory) {
+	if (!M || !sequences || !n) return;
+	std::vector<const char *> ptr(n);
+	std::vector<size_t> len(n);
+	for (size_t i = 0; i < n; i++) ptr[i] = sequences[i].S, len[i] = sequences[i].len;
+	int devices[64];
+	const int nd = compat_devices(devices, 64);
+	const bool show = (&FLAGS != nullptr) && (FLAGS & 128);	 // F_PRINT_PROGRESS, src/global.h:65
+	const double p = (&ANCHOR_P_VALUE != nullptr) ? ANCHOR_P_VALUE : 0.025;
+	const int model_id = (&MODEL != nullptr) ? MODEL : g_compat_model;
+	if (show) compat_progress(0, n * n - n, &n);
+	char msg[512];
+	static_assert(sizeof(model) == sizeof(andi_model), "struct model layout");
+	int rc = andi_dist_matrix_multi(devices, nd, ptr.data(), len.data(), n, p, model_id, low_memory, (andi_model *)M,
+									show ? compat_progress : nullptr, &n, msg, sizeof msg);
+	if (rc) {
+		// src/dist_hack.h:53: errx(1, "Failed to create index for %s.", ...)
+		fprintf(stderr, "andi: Failed to create index: %s\n", msg);
+		exit(1);
+	}
+	if (show) fprintf(stderr, ", done.\n");
+}
+
+extern "C" void distMatrix(model *M, const seq_t *sequences, size_t n) { compat_matrix(M, sequences, n, 0); }
+extern "C" void distMatrixLM(model *M, const seq_t *sequences, size_t n) { compat_matrix(M, sequences, n, 1); }
+
+extern "C" void calculate_distances(seq_t *sequences, size_t n) {
+	if (!print_distances || !model_average) {
+		fprintf(stderr, "andi_b200: calculate_distances needs the host program's print_distances / model_average "
+						"(link the reference's io.c and model.c, with -rdynamic)\n");
+		exit(1);
+	}
+	// src/process.c:233-245
+	if (n == 0 || SIZE_MAX / sizeof(model) / n < n) {
+		fprintf(stderr, "andi: Comparison is limited to %zu sequences (%zu given).\n", (size_t)sqrt((double)(SIZE_MAX / sizeof(model))), n);
+		exit(1);
+	}
+	model *M = (model *)malloc(n * n * sizeof(model));
+	if (!M) {
+		fprintf(stderr, "andi: Could not allocate enough memory for the comparison matrix. Try using --join or --low-memory.\n");
+		exit(errno ? errno : 1);
+	}
+	const int flags = (&FLAGS != nullptr) ? FLAGS : 0;
+	compat_matrix(M, sequences, n, (flags & 32) != 0);	// F_LOW_MEMORY
+	print_distances(M, sequences, n, 1);
+	if ((flags & 2) && print_coverages) print_coverages(M, n);	// F_VERBOSE
+	// src/process.c:289-321: bootstrap matrices from the averaged cells, through the host's own sampler
+	if (&BOOTSTRAP != nullptr && BOOTSTRAP && model_bootstrap) {
+		model *B = (model *)malloc(n * n * sizeof(model));
+		if (!B) {
+			fprintf(stderr, "andi: Out of memory\n");
+			exit(errno ? errno : 1);
+		}
+		while (BOOTSTRAP--) {
+			for (size_t i = 0; i < n; i++) {
+				for (size_t j = i; j < n; j++) {
+					if (i == j) {
+						memset(&B[i * n + j], 0, sizeof(model));
+						B[i * n + j].seq_len = 1, B[i * n + j].counts[0] = 1;
+						continue;
+					}
+					model datum = model_average(&M[i * n + j], &M[j * n + i]);
+					datum = model_bootstrap(datum);
+					B[j * n + i] = B[i * n + j] = datum;
+				}
+			}
+			print_distances(B, sequences, n, 0);
+		}
+		free(B);
+	}
+	free(M);
 }

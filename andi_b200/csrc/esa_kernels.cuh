@@ -264,10 +264,11 @@ __global__ void k_presence_patch(TextView rs, int K, PresenceLevels lv, u32 firs
 // what a lookup of an ABSENT k-mer returns. It does not depend on the last character, so one
 // thread serves the four k-mers 4y..4y+3 of a (K-1)-mer y: one probe sequence, one 32-byte
 // directory read, and the four entries of the walk's own directory view (fdir, see
-// sa_bucket.cuh: tag 0 + plen / tag 1 + text position of the only suffix / tag 2 + the text positions of
+// sa_bucket.cuh: tag 0 + plen / tag 1 + text position of the only suffix and the 15 bases that follow the k-mer
+// there / tag 2 + the text positions of
 // both suffixes / tag 3 + first index and count) in the same pass. Runs once the suffix array is final.
 __global__ void k_prefix_len(PresenceLevels lv, int K, const u64 *__restrict__ dir, const u32 *__restrict__ SA,
-							 unsigned char *__restrict__ plen, u64 *__restrict__ fdir) {
+							 const u64 *__restrict__ code, unsigned char *__restrict__ plen, u64 *__restrict__ fdir) {
 	u32 y = blockIdx.x * blockDim.x + threadIdx.x;
 	if (y >= (1u << (2 * (K - 1)))) return;
 	u32 l = 0;
@@ -287,8 +288,12 @@ __global__ void k_prefix_len(PresenceLevels lv, int K, const u64 *__restrict__ d
 		u32 first = (u32)de[c], count = (u32)(de[c] >> 32);
 		if (count == 0)
 			out[c] = l;
-		else if (count == 1)
-			out[c] = (1ULL << 62) | SA[first];
+		else if (count == 1) {
+			// the only suffix: its position and the 15 bases behind the k-mer there (whatever the
+			// plane holds: the walk cuts every compare at '#' / the text end by position)
+			const u32 p = SA[first];
+			out[c] = (1ULL << 62) | ((window32(code, p + (u32)K) & 0x3fffffffULL) << 31) | p;
+		}
 		else if (count == 2)
 			out[c] = (2ULL << 62) | ((u64)SA[first + 1] << 31) | SA[first];
 		else

@@ -172,7 +172,7 @@ static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
 		k_presence_patch<<<1, 32, 0, st>>>(rs, K, E->present, E->n >= k ? E->n - k : 0, k + 1);
 		k_presence_patch<<<1, 32, 0, st>>>(rs, K, E->present, E->N >= k ? E->N - k : 0, k + 1);
 	}
-	k_prefix_len<<<nblocks((size_t)1 << (2 * (K - 1)), 256), 256, 0, st>>>(E->present, K, E->dir, E->SA, E->plen, E->fdir);
+	k_prefix_len<<<nblocks((size_t)1 << (2 * (K - 1)), 256), 256, 0, st>>>(E->present, K, E->dir, E->SA, E->code, E->plen, E->fdir);
 	ctx->st.esa_launches += 3 + (K - 2);
 	return ANDI_OK;
 }

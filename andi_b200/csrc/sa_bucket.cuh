@@ -341,8 +341,10 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 // ONE table access (the tables compete with the streaming queries for L2):
 //   tag 0 (absent k-mer)    low bits = plen: the longest prefix of the k-mer present in RS, which
 //                           is all the walk needs (no anchor can result below K)
-//   tag 1 (one suffix)      low 32 bits = its text position: the compare starts without the
-//                           dependent suffix-array load
+//   tag 1 (one suffix)      bits 0..30 = its text position, bits 31..60 = the 15 bases that follow
+//                           the k-mer there: k_walk_v3 reads the match length up to K + 15 off the
+//                           entry (no candidate window at all), k_walk_chunks_fast starts its compare
+//                           without the dependent suffix-array load
 //   tag 2 (two suffixes)    bits 0..30 and 31..61 = their text positions in suffix order (N < 2^31):
 //                           most buckets with company hold exactly two, no suffix-array load either
 //   tag 3 (three or more)   low 32 bits = first SA index, bits 32..61 = their number

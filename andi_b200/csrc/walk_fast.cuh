@@ -270,7 +270,7 @@ k_walk_chunks_fast(const SubjectIndex S, const QueryView *__restrict__ queries, 
 				R.found = 0, R.len = (u32)fe, R.s = 0, R.mm = 0;
 				op = OP_DECIDE;
 			} else if (tag == 1u) {	 // one suffix starts with this k-mer: compare it right away
-				u32 p = (u32)fe, rem = qlen - a_pos;
+				u32 p = (u32)fe & 0x7fffffffu, rem = qlen - a_pos;
 				u32 run = SPEC ? N - p : (p < mid ? mid - p : (p == mid ? 0u : N - p));
 				L.cand = 0, L.hi = 1;
 				C.cs = p, C.ck = 0, C.clim = min(rem, run), C.is_cand = 1;

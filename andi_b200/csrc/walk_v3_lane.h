@@ -36,7 +36,7 @@
 #endif
 
 enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V3_SVC_DONE = 4 };
-enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND = 3, V3_CAND1 = 4, V3_CAND2 = 5 };
+enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND1 = 3, V3_CAND2 = 4 };
 
 #define V3_EVEN 0x5555555555555555ULL
 #define V3_MAX_T 31u	   // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
@@ -155,24 +155,27 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 
 	const u32 job = L.job;
 	const u32 end_q = L.lq + L.ll, end_s = L.ls + L.ll;
-	const bool is_step = job == V3_STEP, is_ext = job == V3_EXT, is_cols = job == V3_COLS, is_cand = job >= V3_CAND;
+	const bool is_step = job == V3_STEP, is_ext = job == V3_EXT, is_cols = job == V3_COLS, is_cand = job >= V3_CAND1;
 	const u32 g = L.pos - end_q;	 // process.c:88-89, gap = advance - last.length (pos_Q is fixed while a step lasts)
 	const u32 guess = end_s + g;	 // process.c:91: last.pos_S + advance
-	const bool lucky = is_step && g <= t && guess < c.N;
-	// a directory candidate on the diagonal of the last anchor and close behind it would pair with
-	// it (process.c:167-169): compare it through a window that starts at the end of the last anchor,
-	// like a lucky attempt, so that its gap columns are at hand
+	// The window starts at the END OF THE LAST ANCHOR whenever the gap to pos_Q fits (g <= V3_MAX_T),
+	// lucky attempt (process.c:93: g <= t) or not: the diagonal compare is then at hand for a
+	// directory candidate that turns out to lie on this diagonal, together with its gap columns.
+	const bool diag_ok = is_step && g <= V3_MAX_T && guess < c.N;
+	const bool lucky = diag_ok && g <= t;
+	// CAND1 / CAND2 (the two suffixes of a tag-2 directory entry): the one on the diagonal of the
+	// last anchor would pair with it (process.c:167-169), so it is compared through the same window
 	const bool diag = is_cand && g <= V3_MAX_T && L.cand_p - end_s == g;
-	const bool from_end = is_ext || lucky || diag;
+	const bool from_end = is_ext || diag_ok || diag;
 	// COLS: the gap columns of an anchor that paired over more than V3_MAX_T columns, 32 per trip;
 	// they end where the anchor (already the "last" one) begins, L.len1 of them are left
 	const u32 wq = from_end ? end_q : (is_cols ? L.lq - L.len1 : L.pos);
 	const u32 ws = from_end ? end_s : (is_cols ? L.ls - L.len1 : (is_cand ? L.cand_p : 0u));
-	const u32 gg = (lucky || diag) ? g : 0u;  // columns of the window in front of the compare
+	const u32 gg = (diag_ok || diag) ? g : 0u;	// columns of the window in front of the compare
 	const u32 cq = wq + gg, cs = ws + gg;
 	const u32 run = cs < c.mid ? c.mid - cs : (cs == c.mid ? 0u : c.N - cs);
 	const u32 rem = L.qlen - cq;
-	const u32 clim = (is_step && !lucky) ? 0u : (rem < run ? rem : run);
+	const u32 clim = (is_step && !diag_ok) ? 0u : (rem < run ? rem : run);
 
 	u64 q0, q1, s0, s1;
 	v3_window64(L.q_code, wq, q0, q1);
@@ -187,7 +190,7 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	// ---- what the window decides. Deliberately written as selects, not as if-blocks: every branch
 	// region runs with the few lanes that need it while the rest of the warp waits (the first form
 	// of this kernel spent two thirds of its issue slots that way).
-	const bool c0 = job == V3_CAND, c1 = job == V3_CAND1, c2 = job == V3_CAND2;
+	const bool c1 = job == V3_CAND1, c2 = job == V3_CAND2;
 	const u32 l1 = L.len1;
 	// EXT: the anchor grows; done when the window saw its end
 	L.ll += is_ext ? matched : 0u;
@@ -198,10 +201,11 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	const bool slow_long = (c1 && !complete) || (c2 && !complete && l1 >= matched);
 	const bool tie = c2 && l1 == matched, first_better = c2 && l1 > matched;
 	u32 cur_s = is_cand ? (first_better ? L.cand2 : L.cand_p) : guess;
-	const bool in_window = (lucky || diag) && !first_better;
+	bool in_window = (diag_ok || diag) && !first_better;
+	bool complete_a = complete;	 // the anchor (if any) ends inside what has been compared
 	matched = first_better ? l1 : matched;
-	const bool cand_final = (c0 || c2) && !slow_long;
-	const bool anchor = is_step ? (lucky && matched >= t) : (cand_final && !tie && matched >= t);
+	const bool cand_final = c2 && !slow_long;
+	bool anchor = is_step ? (lucky && matched >= t) : (cand_final && !tie && matched >= t);
 	bool plain_end = cand_final && !anchor;	 // process.c:122: no anchor, pos_Q += length + 1
 	const bool lookup = is_step && !anchor;
 	{
@@ -239,12 +243,26 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 			// tag 0, absent k-mer: only the length matters (it is < K <= threshold)
 			plain_end = tag == 0u, matched = (u32)fe;
 			if (tag == 0u) V3_STAT(tag0);
-			// tag 1: the only suffix; tag 2: two suffixes, both text positions in the entry -- the
-			// one that could pair goes last so that its window is the one at hand when the anchor
-			// is accounted
-			const u32 p1 = (u32)fe & 0x7fffffffu, p2 = (u32)(fe >> 31) & 0x7fffffffu;
+			// tag 1, ONE suffix carries the k-mer: the entry holds its text position and the 15 bases
+			// that follow the k-mer there, so the match length up to K + 15 (>= threshold) comes out
+			// of the entry -- no candidate window, no second trip. A match that long is an anchor at
+			// once (a single candidate is always unique, process.c:122) and grows in EXT trips.
+			const u32 p1 = (u32)fe & 0x7fffffffu;
+			if (tag == 1u) {
+				V3_STAT(tag1);
+				const u32 x = ((u32)(kw >> (2 * c.K)) ^ (u32)(fe >> 31)) & 0x3fffffffu;
+				const u32 d = v3_ctz32(x) >> 1;	 // 16 when all 15 agree
+				const u32 prun = p1 < c.mid ? c.mid - p1 : (p1 == c.mid ? 0u : c.N - p1), prem = L.qlen - L.pos;
+				const u32 plim = prem < prun ? prem : prun, have = (u32)c.K + (d < 15u ? d : 15u);
+				matched = have < plim ? have : plim;
+				complete_a = d < 15u || have >= plim;
+				anchor = matched >= t, plain_end = !anchor;
+				cur_s = p1, in_window = diag_ok && p1 == guess;
+			}
+			// tag 2: two suffixes, both text positions in the entry -- the one that could pair goes
+			// last so that its window is the one at hand when the anchor is accounted
+			const u32 p2 = (u32)(fe >> 31) & 0x7fffffffu;
 			const bool p1_diag = p1 - end_s == g;
-			if (tag == 1u) L.cand_p = (u32)fe, L.job = V3_CAND;
 			if (tag == 2u) L.cand_p = p1_diag ? p2 : p1, L.cand2 = p1_diag ? p1 : p2, L.job = V3_CAND1;
 			if (tag == 3u) {
 				V3_STAT(slow_tag3);
@@ -266,15 +284,15 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 			L.sumr += (L.ll & 3u) * sign;
 		}
 		L.ls = cur_s, L.lq = L.pos, L.ll = matched, L.paired = pairs ? 1u : 0u;
-		if (complete) L.pos += matched + 1u;
-		L.job = complete ? V3_STEP : V3_EXT;
+		if (complete_a) L.pos += matched + 1u;
+		L.job = complete_a ? V3_STEP : V3_EXT;
 		if (pairs) {
 			// model.c:309-337 on the g gap columns (g >= 1)
 			if (!in_window) {
 				// more than V3_MAX_T of them, or a window that does not hold them: COLS trips fetch
 				// them before the walk goes on; L.cand2 remembers whether the anchor still grows
 				V3_STAT(wide_pairs);
-				L.len1 = g, L.cand2 = complete ? 0u : 1u, L.job = V3_COLS;
+				L.len1 = g, L.cand2 = complete_a ? 0u : 1u, L.job = V3_COLS;
 			} else if (g == 1u) {
 				col[((((u32)s0 & 3u) << 2) | ((u32)q0 & 3u)) * V3_CELL_STRIDE] += sign;
 			} else {

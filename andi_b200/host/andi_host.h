@@ -64,11 +64,11 @@ typedef struct host_rng host_rng;
 host_rng *host_rng_new(unsigned long seed);
 void host_rng_free(host_rng *r);
 uint32_t host_rng_binomial(host_rng *r, double p, uint32_t n); /* exact: inversion / BTPE */
-andi_model model_bootstrap(host_rng *r, andi_model datum);
+andi_model host_model_bootstrap(host_rng *r, andi_model datum);
 
 /* output.c : src/io.c:246-338 */
-void print_distances(FILE *out, const andi_model *M, const host_seqs *seqs, const host_config *cfg, int warnings,
+void host_print_distances(FILE *out, const andi_model *M, const host_seqs *seqs, const host_config *cfg, int warnings,
 					 int *flags);
-void print_coverages(FILE *out, const andi_model *M, size_t n);
+void host_print_coverages(FILE *out, const andi_model *M, size_t n);
 
 #endif

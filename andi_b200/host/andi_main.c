@@ -289,8 +289,8 @@ int main(int argc, char *argv[]) {
 		errx(1, "Failed to create index: %s", msg);
 	if (show) fprintf(stderr, ", done.\n");
 
-	print_distances(stdout, M, &seqs, &cfg, 1, &cfg.flags);
-	if (cfg.flags & HF_VERBOSE) print_coverages(stdout, M, n);
+	host_print_distances(stdout, M, &seqs, &cfg, 1, &cfg.flags);
+	if (cfg.flags & HF_VERBOSE) host_print_coverages(stdout, M, n);
 
 	if (cfg.bootstrap) {
 		/* src/process.c:289-321 */
@@ -306,11 +306,11 @@ int main(int argc, char *argv[]) {
 						continue;
 					}
 					andi_model datum = model_average(&M[i * n + j], &M[j * n + i]);
-					datum = model_bootstrap(rng, datum);
+					datum = host_model_bootstrap(rng, datum);
 					B[i * n + j] = B[j * n + i] = datum;
 				}
 			}
-			print_distances(stdout, B, &seqs, &cfg, 0, &cfg.flags);
+			host_print_distances(stdout, B, &seqs, &cfg, 0, &cfg.flags);
 		}
 		free(B);
 		host_rng_free(rng);

@@ -218,7 +218,7 @@ uint32_t host_rng_binomial(host_rng *r, double p, uint32_t n) {
 	return flip ? n - k : k;
 }
 
-andi_model model_bootstrap(host_rng *r, andi_model datum) {
+andi_model host_model_bootstrap(host_rng *r, andi_model datum) {
 	size_t nucl = total(&datum);
 	double p[16], norm = 0.0, used_p = 0.0;
 	for (int k = 0; k < 16; k++) p[k] = datum.counts[k] / (double)nucl, norm += p[k];

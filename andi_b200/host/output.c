@@ -6,7 +6,7 @@
 #include <math.h>
 #include <stdlib.h>
 
-void print_distances(FILE *out, const andi_model *M, const host_seqs *seqs, const host_config *cfg, int warnings,
+void host_print_distances(FILE *out, const andi_model *M, const host_seqs *seqs, const host_config *cfg, int warnings,
 					 int *flags) {
 	const size_t n = seqs->size;
 	double *D = malloc(n * n * sizeof *D);
@@ -45,7 +45,7 @@ void print_distances(FILE *out, const andi_model *M, const host_seqs *seqs, cons
 	free(D);
 }
 
-void print_coverages(FILE *out, const andi_model *M, size_t n) {
+void host_print_coverages(FILE *out, const andi_model *M, size_t n) {
 	/* src/io.c:329-338 */
 	fprintf(out, "\nCoverage:\n");
 	for (size_t i = 0; i < n; i++) {

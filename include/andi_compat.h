@@ -64,11 +64,34 @@ typedef struct model {
 	unsigned int seq_len;
 } model;
 
+/* src/sequence.h:19-26 */
+typedef struct seq_s {
+	char *S;
+	size_t len;
+	char *name;
+} seq_t;
+
 int esa_init(esa_s *C, const seq_subject *S);
 void esa_free(esa_s *C);
 lcp_inter_t get_match(const esa_s *C, const char *query, size_t qlen);
 lcp_inter_t get_match_cached(const esa_s *C, const char *query, size_t qlen);
 model dist_anchor(const esa_s *C, const char *query, size_t query_length, size_t threshold);
+
+/* The driver level (SURVEY 8b "the real offload point"): distMatrix / distMatrixLM
+ * (src/dist_hack.h:34-96) fill M[n * n] for all subjects through ONE batched GPU run -- pool packed
+ * once, subjects spread over the devices of ANDI_B200_DEVICES (e.g. "0-7"; default: the device of
+ * ANDI_B200_DEVICE, else 0) -- and print the reference's progress line when FLAGS has
+ * F_PRINT_PROGRESS. They read the host program's globals ANCHOR_P_VALUE, MODEL and FLAGS
+ * (src/global.h:20-48; link the program with -rdynamic so the library sees them). The two differ
+ * only in what they promise about memory; one index is resident per GPU in both.
+ * calculate_distances (src/process.h:11, src/process.c:230-321) is the reference's own sequence:
+ * allocate M, fill it, print_distances / print_coverages / bootstrap matrices through the HOST
+ * PROGRAM's own io.c and model.c (print_distances, print_coverages, model_average,
+ * model_bootstrap are taken from the executable). With it src/esa.c and src/process.c can be
+ * dropped from the reference's build altogether. */
+void distMatrix(model *M, const seq_t *sequences, size_t n);
+void distMatrixLM(model *M, const seq_t *sequences, size_t n);
+void calculate_distances(seq_t *sequences, size_t n);
 
 /* Used when the hosting executable does not define the reference's global `int MODEL`. */
 void andi_compat_set_model(int model_id);

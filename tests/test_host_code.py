@@ -37,8 +37,10 @@ def host():
     L.seqs_free.argtypes = [C.POINTER(HostSeqs)]
     L.host_rng_new.restype = C.c_void_p
     L.host_rng_new.argtypes = [C.c_ulong]
-    L.model_bootstrap.restype = native.Model
-    L.model_bootstrap.argtypes = [C.c_void_p, native.Model]
+    L.host_model_bootstrap.restype = native.Model
+    L.host_model_bootstrap.argtypes = [C.c_void_p, native.Model]
+    L.host_rng_binomial.restype = C.c_uint32
+    L.host_rng_binomial.argtypes = [C.c_void_p, C.c_double, C.c_uint32]
     return L
 
 
@@ -113,7 +115,63 @@ def test_bootstrap_is_a_multinomial_resample(host):
     counts = [24436, 80, 94, 70, 83, 24432, 77, 85, 78, 87, 24406, 88, 84, 85, 81, 25720]
     m = native.Model((C.c_uint32 * 16)(*counts), 100000)
     rng = host.host_rng_new(42)
-    draws = np.array([list(host.model_bootstrap(rng, m).counts) for _ in range(400)], dtype=np.float64)
+    draws = np.array([list(host.host_model_bootstrap(rng, m).counts) for _ in range(400)], dtype=np.float64)
     assert (draws.sum(axis=1) == sum(counts)).all()  # src/model.c:222-232: N is preserved
     mean, want = draws.mean(axis=0), np.array(counts, dtype=np.float64)
     assert np.all(np.abs(mean - want) < 5 * np.sqrt(want) / np.sqrt(400) + 1.0)
+
+
+@pytest.mark.parametrize("n,p", [(7, 0.3), (40, 0.02), (25, 0.5), (200, 0.1), (1000, 0.031), (1000, 0.47), (5000, 0.9),
+                                 (100000, 0.0004), (100000, 0.25), (2100000, 0.0125), (2100000, 0.245), (4000000000, 1e-6)])
+def test_binomial_sampler_is_exact(host, n, p):
+    """The bootstrap's binomial draws (inversion below a mean of 30, BTPE above) against the exact
+    binomial pmf: chi-square goodness of fit over the bins that carry the mass, plus mean and
+    variance. (The reference draws the same distribution through gsl_ran_binomial; its random
+    stream cannot be reproduced without GSL, so the distribution is what is pinned here.)"""
+    from scipy import stats
+
+    draws = 40000
+    rng = host.host_rng_new(n % 1000 + int(p * 1e6))
+    x = np.array([host.host_rng_binomial(rng, p, n) for _ in range(draws)], dtype=np.int64)
+    assert x.min() >= 0 and x.max() <= n
+    mean, var = n * p, n * p * (1 - p)
+    assert abs(x.mean() - mean) < 5 * np.sqrt(var / draws)
+    assert abs(x.var() - var) < 6 * var * np.sqrt(2.0 / draws) + 5 * np.sqrt(var / draws)
+    # bins: equal-probability classes from the exact quantiles (at most 60 of them)
+    dist = stats.binom(n, p)
+    edges = np.unique(dist.ppf(np.linspace(0, 1, 61)[1:-1]).astype(np.int64))
+    cdf = np.concatenate([[0.0], dist.cdf(edges), [1.0]])
+    expect = np.diff(cdf) * draws
+    observed = np.bincount(np.searchsorted(edges, x, side="left"), minlength=len(edges) + 1)
+    keep = expect > 5
+    chi2 = float((((observed - expect) ** 2) / np.where(keep, expect, 1.0))[keep].sum())
+    dof = int(keep.sum()) - 1
+    assert dof >= 1
+    assert chi2 < stats.chi2.ppf(1 - 1e-6, dof), (n, p, chi2, dof)
+
+
+def test_bootstrap_cell_marginals(host):
+    """model_bootstrap (src/model.c:222-232): every cell of the resampled matrix is Binomial(N, c/N),
+    at small and at genome-sized counts; N is preserved."""
+    from scipy import stats
+
+    for counts in ([3, 0, 1, 0, 2, 5, 0, 0, 1, 0, 4, 0, 0, 0, 0, 6],
+                   [524000, 2100, 2300, 1900, 2050, 518000, 2250, 1980, 2010, 2150, 530000, 1890, 2240, 2020, 2060, 526000]):
+        m = native.Model((C.c_uint32 * 16)(*counts), sum(counts))
+        rng = host.host_rng_new(7)
+        reps = 3000
+        draws = np.array([list(host.host_model_bootstrap(rng, m).counts) for _ in range(reps)], dtype=np.float64)
+        assert (draws.sum(axis=1) == sum(counts)).all()
+        N = sum(counts)
+        for k, c in enumerate(counts):
+            pk = c / N
+            if c == 0:
+                assert (draws[:, k] == 0).all()
+                continue
+            var = N * pk * (1 - pk)
+            assert abs(draws[:, k].mean() - c) < 5 * np.sqrt(var / reps) + 1e-9, (k, c)
+            assert abs(draws[:, k].var() - var) < 6 * var * np.sqrt(2.0 / reps) + 5 * np.sqrt(var / reps), (k, c)
+        # two cells are negatively correlated: cov = -N p_i p_j
+        cov = np.cov(draws[:, 0], draws[:, 5])[0, 1]
+        want = -N * (counts[0] / N) * (counts[5] / N)
+        assert abs(cov - want) < 6 * np.sqrt(counts[0] * counts[5]) / np.sqrt(reps) + 1.0

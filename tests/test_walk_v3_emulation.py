@@ -20,7 +20,7 @@ UNIT_WORDS = 38
 CODE = np.full(256, 255, dtype=np.uint8)
 for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3), (b"#", 1)):
     CODE[ch[0]] = v
-STATS = ["trips", "ext_trips", "cand_trips", "steps", "lucky_hits", "lookups", "tag0", "wide_gaps", "slow_steps", "slow_tail", "slow_tag3", "wide_pairs", "slow_long", "cols_trips", "pushes", "drained", "drains", "drain_rounds",
+STATS = ["trips", "ext_trips", "cand_trips", "steps", "lucky_hits", "lookups", "tag0", "tag1", "wide_gaps", "slow_steps", "slow_tail", "slow_tag3", "wide_pairs", "slow_long", "cols_trips", "pushes", "drained", "drains", "drain_rounds",
          "warp_trips", "running_lanes", "services", "served_lanes"]
 
 
@@ -56,7 +56,7 @@ def pack(text: bytes) -> np.ndarray:
 
 def directory_view(rs: bytes, SA: np.ndarray, K: int) -> np.ndarray:
     """fdir of sa_bucket.cuh / esa_kernels.cuh, restated with numpy: per k-mer tag 0 + longest
-    present prefix / tag 1 + text position of its only suffix / tag 2 + the text positions of its two suffixes
+    present prefix / tag 1 + text position of its only suffix and the 15 bases behind the k-mer there / tag 2 + the text positions of its two suffixes
     (31 bits each) / tag 3 + first SA index, count."""
     N, mid = len(rs), len(rs) // 2
     codes = CODE[np.frombuffer(rs, dtype=np.uint8)].astype(np.int64)
@@ -88,7 +88,12 @@ def directory_view(rs: bytes, SA: np.ndarray, K: int) -> np.ndarray:
         plen = np.where(have[prefix], m, plen)
     fdir = np.where(count == 0, plen, 0).astype(np.uint64)
     one = count == 1
-    fdir[one] = (np.uint64(1) << np.uint64(62)) | SA[first[one]].astype(np.uint64)
+    p_one = SA[first[one]].astype(np.int64)
+    nxt = np.zeros(len(p_one), dtype=np.uint64)
+    for j in range(15):  # the 15 bases behind the k-mer (whatever the planes hold there: zero past the end)
+        at = p_one + K + j
+        nxt |= np.where(at < N, codes[np.minimum(at, N - 1)], 0).astype(np.uint64) << np.uint64(2 * j)
+    fdir[one] = (np.uint64(1) << np.uint64(62)) | (nxt << np.uint64(31)) | p_one.astype(np.uint64)
     two = count == 2
     fdir[two] = (np.uint64(2) << np.uint64(62)) | (SA[first[two] + 1].astype(np.uint64) << np.uint64(31)) | SA[first[two]].astype(np.uint64)
     many = count > 2
