@@ -61,6 +61,13 @@ struct andi_ctx {
 
 	unsigned long long *walk_counter = nullptr;  // unit dispenser of the walk kernels
 
+	// Second lane of andi_dist_rows: a helper context on its own stream that BORROWS this pool, so
+	// that the index build and the walk of subject i+1 fill the tail of subject i's walk
+	// (walk_host.cuh). Created on first use, destroyed with its owner.
+	andi_ctx *helper = nullptr;
+	bool borrowed_pool = false;
+	cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+
 	andi_stats st{};
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> esa_ev, walk_ev;
 	std::vector<cudaEvent_t> free_ev;
@@ -196,6 +203,11 @@ extern "C" int andi_ctx_create(int device, void *stream, andi_ctx **out) {
 }
 
 static void pool_release(andi_ctx *ctx) {
+	if (ctx->helper) ctx->helper->n = 0;  // its borrowed pointers die with this pool
+	if (ctx->borrowed_pool) {
+		ctx->pool_code = ctx->pool_spec = nullptr, ctx->pool_comp = nullptr, ctx->pool_sep3 = nullptr, ctx->d_queries = nullptr;
+		ctx->borrowed_pool = false;
+	}
 	dfree(ctx, ctx->pool_code);
 	dfree(ctx, ctx->pool_spec);
 	dfree(ctx, ctx->pool_comp);
@@ -209,6 +221,12 @@ static void pool_release(andi_ctx *ctx) {
 extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	if (ctx->helper) {
+		andi_ctx_destroy(ctx->helper);
+		ctx->helper = nullptr;
+	}
+	if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+	if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
 	cudaStreamSynchronize(ctx->stream);
 	harvest_events(ctx);
 	pool_release(ctx);

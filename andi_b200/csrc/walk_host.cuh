@@ -211,9 +211,43 @@ extern "C" int andi_dist_anchor(andi_ctx *ctx, const andi_esa *E, const char *qu
 	return rc;
 }
 
+// The helper lane of a context: same device, own stream, the owner's pool by reference.
+static int helper_ensure(andi_ctx *ctx) {
+	if (!ctx->helper) {
+		andi_ctx *h = nullptr;
+		int rc = andi_ctx_create(ctx->device, nullptr, &h);
+		if (rc) {
+			ctx->err = std::string("helper lane: ") + andi_last_error(nullptr);
+			return rc;
+		}
+		ctx->helper = h;
+		CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
+	}
+	andi_ctx *h = ctx->helper;
+	h->n = ctx->n, h->len = ctx->len, h->gc = ctx->gc, h->has_sep = ctx->has_sep, h->word_off = ctx->word_off;
+	h->pool_code = ctx->pool_code, h->pool_spec = ctx->pool_spec, h->pool_words = ctx->pool_words;
+	h->pool_comp = ctx->pool_comp, h->pool_sep3 = ctx->pool_sep3, h->d_queries = ctx->d_queries, h->any_sep = ctx->any_sep;
+	h->borrowed_pool = true;
+	return ANDI_OK;
+}
+
+static void merge_stats(andi_stats &a, const andi_stats &b) {
+	a.esa_ms += b.esa_ms, a.walk_ms += b.walk_ms;
+	a.esa_launches += b.esa_launches, a.cub_calls += b.cub_calls, a.walk_launches += b.walk_launches;
+	a.pairs += b.pairs, a.subjects += b.subjects, a.sa_rounds += b.sa_rounds;
+	a.h2d_bytes += b.h2d_bytes, a.d2h_bytes += b.d2h_bytes, a.p2p_bytes += b.p2p_bytes;
+}
+
+// Two subjects are in flight, on two streams ("lanes"): while the walk of subject i drains its last
+// units -- a persistent grid whose tail leaves SMs idle -- the index build and the first walk
+// blocks of subject i+1 take the free SMs. Every lane has its own index arrays, build scratch and
+// unit records (lane 1 is a helper context that borrows the pool); within a lane everything is
+// stream-ordered, so the only cross-lane synchronisation is fork / join around the whole call.
+// ANDI_B200_LANES=1 keeps everything on the context's own stream (used to time kernels alone).
 static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_value, int model, int low_memory,
 						  andi_model *out, bool out_on_device) {
-	(void)low_memory;  // one index is resident at a time in either mode (src/dist_hack.h:14-16)
+	(void)low_memory;  // one index is resident per lane in either mode (src/dist_hack.h:14-16)
 	if (!ctx || !out || s_begin > s_end || s_end > ctx->n) return ANDI_ERR_ARG;
 	if (s_begin == s_end) return ANDI_OK;
 	CK(cudaSetDevice(ctx->device));
@@ -221,50 +255,93 @@ static int dist_rows_impl(andi_ctx *ctx, size_t s_begin, size_t s_end, double p_
 	WalkPlan plan = plan_walk(ctx, ctx->len);
 	unsigned long long total_bases = 0;
 	for (size_t l : ctx->len) total_bases += l;
-	u32 *d_rec = nullptr, *d_out = nullptr;
-	CK(dalloc(ctx, &d_rec, plan.record_words));
+	const char *lanes_env = getenv("ANDI_B200_LANES");
+	int nl = (lanes_env && atoi(lanes_env) == 1) || rows < 2 ? 1 : 2;
+	u32 *d_out = nullptr;
 	if (out_on_device)
 		d_out = (u32 *)out;
 	else
 		CK(dalloc(ctx, &d_out, rows * n * 17));
+	const bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
 	int rc = ANDI_OK;
-	andi_esa E;	 // rebuilt in place for every subject: its arrays are allocated once
-	E.ctx = ctx;
-	for (size_t i = s_begin; i < s_end && !rc; i++) {
-		E.n = (u32)ctx->len[i];
-		E.N = 2 * E.n + 1;
-		E.has_sep = ctx->has_sep[i] != 0;
-		E.self = (u32)i;
-		E.threshold = (u32)andi_threshold(p_value, ctx->gc[i], E.N);
-		E.K = choose_depth(E.N, E.threshold, total_bases);
-		size_t nw = plane_words(E.N);
-		rc = esa_ensure(ctx, &E);
-		if (!rc) {
-			k_build_rs<<<nblocks(nw, 256), 256, 0, ctx->stream>>>(ctx->pool_code + ctx->word_off[i],
-																   ctx->pool_spec + ctx->word_off[i], E.n, E.code,
-																   E.spec, (u32)nw);
-			ctx->st.esa_launches++;
-			rc = build_index(ctx, &E, ANDI_ESA_SEARCH);
-		}
-		if (!rc) {
-			SubjectIndex S = subject_index(&E);
-			S.qspec_delta = ctx->pool_spec - ctx->pool_code;
-			rc = launch_walk(ctx, S, ctx->d_queries, nullptr, (u32)n, plan, E.threshold, model,
-							 ctx->any_sep || E.has_sep, true, d_rec, d_out + (i - s_begin) * n * 17);
+	if (nl == 2) {
+		// the lazily built pool tables must exist before the helper borrows the pool
+		if (!quarter) rc = pool_comp_ensure(ctx);
+		if (!rc && ctx->any_sep) rc = pool_sep3_ensure(ctx);
+		if (!rc) rc = helper_ensure(ctx);
+		if (rc) nl = 1, rc = ANDI_OK;  // no second lane: carry on with one
+	}
+	andi_ctx *lane[2] = {ctx, nl == 2 ? ctx->helper : nullptr};
+	if (nl == 2) {
+		CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+		CK(cudaStreamWaitEvent(lane[1]->stream, ctx->fork_ev, 0));
+	}
+	cudaEvent_t e_begin = get_event(ctx), e_end = get_event(ctx);
+	mark(ctx, e_begin);
+	u32 *d_rec[2] = {nullptr, nullptr};
+	andi_esa E[2];	// rebuilt in place for every subject of the lane: the arrays are allocated once
+	for (int x = 0; x < nl && !rc; x++) {
+		E[x].ctx = lane[x];
+		if (dalloc(lane[x], &d_rec[x], plan.record_words) != cudaSuccess) {
+			ctx->err = "device allocation failed (walk records)";
+			rc = ANDI_ERR_NOMEM;
 		}
 	}
-	esa_release(&E);
+	for (size_t i = s_begin; i < s_end && !rc; i++) {
+		const int x = (int)((i - s_begin) % (size_t)nl);
+		andi_ctx *L = lane[x];
+		andi_esa &Ex = E[x];
+		Ex.n = (u32)ctx->len[i];
+		Ex.N = 2 * Ex.n + 1;
+		Ex.has_sep = ctx->has_sep[i] != 0;
+		Ex.self = (u32)i;
+		Ex.threshold = (u32)andi_threshold(p_value, ctx->gc[i], Ex.N);
+		Ex.K = choose_depth(Ex.N, Ex.threshold, total_bases);
+		size_t nw = plane_words(Ex.N);
+		rc = esa_ensure(L, &Ex);
+		if (!rc) {
+			k_build_rs<<<nblocks(nw, 256), 256, 0, L->stream>>>(ctx->pool_code + ctx->word_off[i], ctx->pool_spec + ctx->word_off[i],
+																 Ex.n, Ex.code, Ex.spec, (u32)nw);
+			L->st.esa_launches++;
+			rc = build_index(L, &Ex, ANDI_ESA_SEARCH);
+		}
+		if (!rc) {
+			SubjectIndex S = subject_index(&Ex);
+			S.qspec_delta = ctx->pool_spec - ctx->pool_code;
+			rc = launch_walk(L, S, ctx->d_queries, nullptr, (u32)n, plan, Ex.threshold, model, ctx->any_sep || Ex.has_sep, true,
+							 d_rec[x], d_out + (i - s_begin) * n * 17);
+		}
+		if (rc && L != ctx) ctx->err = L->err;
+	}
+	for (int x = 0; x < nl; x++) {
+		esa_release(&E[x]);
+		dfree(lane[x], d_rec[x]);
+	}
+	if (nl == 2) {
+		cudaEventRecord(ctx->join_ev, lane[1]->stream);
+		cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0);
+	}
+	mark(ctx, e_end);
 	if (!rc && !out_on_device) {
 		CK(cudaMemcpyAsync(out, d_out, rows * n * sizeof(andi_model), cudaMemcpyDeviceToHost, ctx->stream));
 		ctx->st.d2h_bytes += rows * n * sizeof(andi_model);
 	}
 	cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	if (nl == 2 && e == cudaSuccess) e = cudaStreamSynchronize(lane[1]->stream);
 	if (!rc && e != cudaSuccess) {
 		ctx->err = std::string("walk: ") + cudaGetErrorString(e);
 		rc = ANDI_ERR_CUDA;
 	}
 	harvest_events(ctx);
-	dfree(ctx, d_rec);
+	if (nl == 2) {
+		harvest_events(lane[1]);
+		merge_stats(ctx->st, lane[1]->st);
+		lane[1]->st = andi_stats{};
+	}
+	// wall time of the whole call on the device (the per-kernel sums above overlap across lanes)
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, e_begin, e_end) == cudaSuccess) ctx->st.rows_ms += ms;
+	ctx->free_ev.push_back(e_begin), ctx->free_ev.push_back(e_end);
 	if (!out_on_device) dfree(ctx, d_out);
 	return rc;
 }

@@ -41,12 +41,20 @@ class LcpInter(C.Structure):
     _fields_ = [("l", C.c_int32), ("i", C.c_int32), ("j", C.c_int32), ("m", C.c_int32)]
 
 
+class PoolView(C.Structure):
+    """andi_pool_view: the packed pool of a context (device pointers + per-sequence facts)."""
+
+    _fields_ = [("d_code", C.c_void_p), ("d_spec", C.c_void_p), ("words", C.c_size_t), ("n", C.c_size_t),
+                ("lens", C.POINTER(C.c_size_t)), ("gc", C.POINTER(C.c_double)), ("has_separator", C.POINTER(C.c_int)),
+                ("any_separator", C.c_int)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("esa_ms", C.c_double), ("walk_ms", C.c_double), ("total_ms", C.c_double),
         ("esa_launches", C.c_uint64), ("cub_calls", C.c_uint64), ("walk_launches", C.c_uint64), ("pairs", C.c_uint64),
         ("subjects", C.c_uint64), ("sa_rounds", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("p2p_bytes", C.c_uint64),
+        ("p2p_bytes", C.c_uint64), ("rows_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -92,6 +100,11 @@ def load() -> C.CDLL:
     L.andi_dist_anchor.argtypes = [vp, vp, C.c_char_p, sz, sz, C.c_int, C.POINTER(Model)]
     L.andi_dist_rows.argtypes = [vp, sz, sz, C.c_double, C.c_int, C.c_int, vp]
     L.andi_dist_rows_device.argtypes = [vp, sz, sz, C.c_double, C.c_int, C.c_int, vp]
+    L.andi_pool_export.argtypes = [vp, C.POINTER(PoolView)]
+    L.andi_pool_import.argtypes = [vp, C.POINTER(PoolView), C.c_int]
+    L.andi_device_count.argtypes = []
+    L.andi_dist_matrix_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_char_p), C.POINTER(sz), sz, C.c_double, C.c_int,
+                                         C.c_int, vp, vp, vp, C.c_char_p, sz]
     L.andi_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.andi_reset_stats.argtypes = [vp]
     L.andi_reset_stats.restype = None
@@ -175,6 +188,30 @@ class Context:
         self._ck(load().andi_pool_set_device(self.h, C.c_void_p(dev_ptr), offs, ls, n))
         self.n = n
 
+    def pool_export(self) -> dict:
+        """The packed pool as plain values: device pointers of the two planes (on this context's
+        device), their length in u64 words, and the per-sequence facts as numpy arrays."""
+        v = PoolView()
+        self._ck(load().andi_pool_export(self.h, C.byref(v)))
+        n = v.n
+        return {"d_code": v.d_code, "d_spec": v.d_spec, "words": v.words, "n": n,
+                "lens": np.ctypeslib.as_array(v.lens, (n,)).astype(np.uint64).copy(),
+                "gc": np.ctypeslib.as_array(v.gc, (n,)).copy(),
+                "has_separator": np.ctypeslib.as_array(v.has_separator, (n,)).astype(np.int32).copy(),
+                "any_separator": bool(v.any_separator)}
+
+    def pool_import(self, view: dict, src_device: int = -1):
+        """Adopt a packed pool (a copy of its planes): from another context of this process
+        (src_device = its device: peer copy) or from planes already on this device (-1)."""
+        n = int(view["n"])
+        lens = (C.c_size_t * n)(*[int(x) for x in view["lens"]])
+        gc = (C.c_double * n)(*[float(x) for x in view["gc"]])
+        sep = (C.c_int * n)(*[int(x) for x in view["has_separator"]])
+        v = PoolView(C.c_void_p(view["d_code"]), C.c_void_p(view["d_spec"]) if view.get("d_spec") else None, int(view["words"]), n,
+                     lens, gc, sep, int(bool(view["any_separator"])))
+        self._ck(load().andi_pool_import(self.h, C.byref(v), src_device))
+        self.n = n
+
     def pool_info(self, k: int):
         ln, gc, sep = C.c_size_t(), C.c_double(), C.c_int()
         self._ck(load().andi_pool_info(self.h, k, C.byref(ln), C.byref(gc), C.byref(sep)))
@@ -237,3 +274,20 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def dist_matrix_multi(devices, seqs, p_value: float = 0.025, model: str = "JC", low_memory: bool = False) -> np.ndarray:
+    """andi_dist_matrix_multi: the whole matrix on several GPUs of this process (one host thread
+    per device, pool packed once and copied to the peers, subjects from a shared queue)."""
+    seqs = [bytes(s) for s in seqs]
+    n = len(seqs)
+    arr = (C.c_char_p * n)(*seqs)
+    lens = (C.c_size_t * n)(*[len(s) for s in seqs])
+    dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+    out = np.empty((n, n, 17), np.uint32)
+    msg = C.create_string_buffer(512)
+    rc = load().andi_dist_matrix_multi(dev, len(devices), arr, lens, n, p_value, MODELS[model], int(low_memory),
+                                       C.c_void_p(out.ctypes.data), None, None, msg, 512)
+    if rc:
+        raise AndiError(f"{ERRORS.get(rc, rc)}: {msg.value.decode()}")
+    return out

@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--model", default="")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the whole-matrix (strong scaling) leg")
     ap.add_argument("--cpu-queries", type=int, default=192, help="queries per subject in the bounded CPU sample")
     return ap.parse_args()
 
@@ -240,10 +241,13 @@ def main():
         run_reference(args)
         return
 
+    import ctypes as C
+    import hashlib
+
     import torch
     import torch.distributed as dist
 
-    from andi_b200 import native
+    from andi_b200 import driver, native
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -252,14 +256,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    store = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        # a second store of our own: its add() is the atomic counter of the dynamic subject queue
+        store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 1,
+                              world, is_master=(rank == 0))
 
     g, ln, lo, hi, seed, model = workload_of(args)
     chars, offsets, lens, d = make_pool_device(g, ln, lo, hi, seed, device, args.contigs)
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
+    L = native.load()
     ctx = native.Context(local, stream.cuda_stream)
     ctx.set_pool_device(chars.data_ptr(), offsets, lens)
 
@@ -268,8 +277,11 @@ def main():
     out_dev = torch.empty((rows, g, 17), dtype=torch.int32, device=device)
     gathered = torch.empty((world * rows, g, 17), dtype=torch.int32, device=device) if world > 1 else None
 
+    def first_row(step):
+        return ((step * world + rank) * rows) % max(1, g - rows + 1)
+
     def step_device(step):
-        s0 = ((step * world + rank) * rows) % max(1, g - rows + 1)
+        s0 = first_row(step)
         ctx.dist_rows_device(out_dev.data_ptr(), s0, s0 + rows, 0.025, model)
         if world > 1:
             dist.all_gather_into_tensor(gathered, out_dev)
@@ -279,13 +291,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- value: K steps with the pool resident in HBM, device-timed
     for w in range(args.warmup):
         step_device(w)
     barrier()
     ctx.reset_stats()
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for s in range(args.steps):
@@ -293,37 +313,50 @@ def main():
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1))
     st = ctx.stats()
     pairs_per_step_rank = rows * (g - 1)
     value = world * pairs_per_step_rank * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the host-buffer ABI (pinned host pool -> rows on the host)
+    # ---- the dominant kernel timed ALONE: one more step with a single subject in flight
+    # (ANDI_B200_LANES=1), so that no other kernel of ours shares the SMs with the walk
+    os.environ["ANDI_B200_LANES"] = "1"
+    ctx.reset_stats()
+    step_device(args.warmup + args.steps)
+    barrier()
+    st_alone = ctx.stats()
+    del os.environ["ANDI_B200_LANES"]
+
+    # ---- end to end through the host-buffer ABI: pinned host pool -> rows on the host. With
+    # several ranks the pool is uploaded and packed once (rank 0) and its packed planes are
+    # broadcast over NVLink; every rank computes its rows; rank 0 reads all of them back.
     e2e = None
     host_pool = None
     if not args.no_e2e:
-        host_pool = torch.empty(chars.numel(), dtype=torch.uint8, pin_memory=True)
-        host_pool.copy_(chars)
-        torch.cuda.synchronize()
-        base_ptr = host_pool.data_ptr()
-        import ctypes as C
-
         n = g
-        ptrs = (C.c_char_p * n)(*[C.c_char_p(base_ptr + o) for o in offsets])
-        lens_c = (C.c_size_t * n)(*lens)
-        out_host = torch.empty((rows, g, 17), dtype=torch.int32, pin_memory=True)
-        L = native.load()
         ctx2 = native.Context(local, stream.cuda_stream)
+        out_host = torch.empty((world * rows, g, 17), dtype=torch.int32, pin_memory=True) if rank == 0 else None
+        if rank == 0:
+            host_pool = torch.empty(chars.numel(), dtype=torch.uint8, pin_memory=True)
+            host_pool.copy_(chars)
+            torch.cuda.synchronize()
+            base_ptr = host_pool.data_ptr()
+            ptrs = (C.c_char_p * n)(*[C.c_char_p(base_ptr + o) for o in offsets])
+            lens_c = (C.c_size_t * n)(*lens)
 
         def step_e2e(step):
-            s0 = ((step * world + rank) * rows) % max(1, g - rows + 1)
-            ctx2._ck(L.andi_pool_set_host(ctx2.h, ptrs, lens_c, n))
-            ctx2.n = n
-            ctx2._ck(L.andi_dist_rows(ctx2.h, s0, s0 + rows, 0.025, native.MODELS[model], 0, C.c_void_p(out_host.data_ptr())))
+            s0 = first_row(step)
+            if rank == 0:
+                ctx2._ck(L.andi_pool_set_host(ctx2.h, ptrs, lens_c, n))
+                ctx2.n = n
+            if world > 1:
+                driver.broadcast_pool(ctx2, dist, device, rank)
+                ctx2.dist_rows_device(out_dev.data_ptr(), s0, s0 + rows, 0.025, model)
+                dist.all_gather_into_tensor(gathered, out_dev)
+                if rank == 0:
+                    out_host.copy_(gathered, non_blocking=True)
+            else:
+                ctx2._ck(L.andi_dist_rows(ctx2.h, s0, s0 + rows, 0.025, native.MODELS[model], 0, C.c_void_p(out_host.data_ptr())))
 
         step_e2e(0)
         barrier()
@@ -333,43 +366,85 @@ def main():
             step_e2e(1 + s)
         e1.record(stream)
         barrier()
-        ms2 = e0.elapsed_time(e1)
-        t = torch.tensor([ms2], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms2 = float(t.item())
+        ms2 = max_over_ranks(e0.elapsed_time(e1))
         st2 = ctx2.stats()
+        d2h = int(st2["d2h_bytes"] // args.steps) if world == 1 else (world * rows * g * 68 if rank == 0 else 0)
         e2e = {
             "value": world * pairs_per_step_rank * args.steps / (ms2 * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": int(st2["h2d_bytes"] // args.steps), "d2h_bytes_per_step": int(st2["d2h_bytes"] // args.steps),
+            "h2d_bytes_per_step": int(st2["h2d_bytes"] // args.steps), "d2h_bytes_per_step": d2h,
             "ms_per_step": ms2 / args.steps,
+            "pool": "uploaded and packed on rank 0, packed planes broadcast with NCCL" if world > 1 else "uploaded and packed on the GPU",
         }
         ctx2.close()
 
-    # ---- roofline of the dominant kernel (the anchor walk)
+    # ---- the whole matrix (strong scaling): all g rows, subjects from a shared queue in batches,
+    # rows summed to rank 0 (disjoint, so the sum is the matrix)
+    full_matrix = None
+    if not args.no_full and (g * g * 68) < 8e9:
+        full = torch.zeros((g, g, 17), dtype=torch.int32, device=device)
+        batch = max(1, min(16, g // (world * 8)))
+        local_next = [0]
+
+        def take(b):
+            if store is not None:
+                return store.add("andi_next_subject", b) - b
+            v = local_next[0]
+            local_next[0] += b
+            return v
+
+        barrier()
+        e0.record(stream)
+        mine = driver.dynamic_rows(ctx, g, full.data_ptr(), take, batch, 0.025, model)
+        if world > 1:
+            dist.reduce(full, dst=0, op=dist.ReduceOp.SUM)
+        e1.record(stream)
+        barrier()
+        ms3 = max_over_ranks(e0.elapsed_time(e1))
+        counts = torch.tensor([mine], dtype=torch.int64, device=device)
+        all_counts = [torch.zeros_like(counts) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(all_counts, counts)
+        else:
+            all_counts = [counts]
+        if rank == 0:
+            digest = hashlib.blake2b(full.cpu().numpy().tobytes(), digest_size=16).hexdigest()
+            full_matrix = {"seconds": ms3 * 1e-3, "pairs_per_s": g * (g - 1) / (ms3 * 1e-3), "rows": g, "queue_batch": batch,
+                           "rows_per_rank": [int(c.item()) for c in all_counts],
+                           # the same digest at every N = the N-GPU matrix is the 1-GPU matrix
+                           "blake2b_of_matrix": digest}
+        del full
+
+    # ---- roofline of the dominant kernel (the anchor walk), from the single-lane step
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
         peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bytes_per_pair = 2 * ln / 4  # query + subject diagonal, 2 bits per base, read once
-    # one "launch" = the chunk kernel plus its small reduce kernel for one subject
-    n_walks = max(1, st["walk_launches"] // 2)
-    walk_ms = st["walk_ms"] / n_walks
-    pairs_per_launch = st["pairs"] / n_walks
+    # one "launch" = the walk kernels of one subject (k_walk_v3<1>, k_walk_v3<2>, k_walk_reduce)
+    n_walks = max(1, st_alone["subjects"])
+    walk_ms = st_alone["walk_ms"] / n_walks
+    pairs_per_launch = st_alone["pairs"] / n_walks
     achieved = pairs_per_launch * bytes_per_pair / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tf = ROOT / "profiles" / "walk_traffic.json"
     if tf.exists() and args.workload == "c4" and not args.genomes and not args.length and not args.contigs:
-        t_ = json.loads(tf.read_text())  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-        traffic = (t_["dram_bytes_read"] + t_["dram_bytes_write"]) * (pairs_per_launch / t_["pairs_per_launch"])
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (tools/capture_traffic.sh);
+        # only a capture of THIS build of the kernels counts
+        t_ = json.loads(tf.read_text())
+        if t_.get("kernel_sha") == kernel_sources_sha():
+            traffic = (t_["dram_bytes_read"] + t_["dram_bytes_write"]) * (pairs_per_launch / t_["pairs_per_launch"])
+            traffic_src = t_.get("capture")
+        else:
+            traffic_src = "profiles/walk_traffic.json is from other kernel sources (%s): ignored" % t_.get("kernel_sha")
     roofline = {
-        "bound": "hbm", "kernel": "k_walk_chunks_fast (+ k_walk_reduce)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "bound": "hbm", "kernel": "k_walk_v3<1> + k_walk_v3<2> + k_walk_reduce (one subject)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "algorithmic_bytes_per_pair": bytes_per_pair, "pairs_per_launch": pairs_per_launch, "launch_ms": walk_ms,
-        "walk_share_of_step": st["walk_ms"] / ms if ms > 0 else None,
+        "timed": "alone, one subject in flight (ANDI_B200_LANES=1); the timed steps run two subjects in flight",
+        "walk_share_of_step": (st_alone["walk_ms"] / st_alone["rows_ms"]) if st_alone["rows_ms"] > 0 else None,
     }
-    esa_mbp_s = st["subjects"] * ln / 1e6 / (st["esa_ms"] * 1e-3) if st["esa_ms"] > 0 else None
+    esa_ms = st_alone["esa_ms"] / n_walks
     esa_bytes = 14 * (2 * ln + 1) + 16.8e6
 
     cpu = parity = None
@@ -413,11 +488,12 @@ def main():
             "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(st["esa_launches"] + st["walk_launches"]),
             "cub_calls": int(st["cub_calls"]),
-            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-            "esa_build": {"mbp_per_s": esa_mbp_s, "ms_per_subject": st["esa_ms"] / max(1, st["subjects"]),
-                          "algorithmic_gbs": (esa_bytes * st["subjects"] / (st["esa_ms"] * 1e-3) / 1e9) if st["esa_ms"] > 0 else None,
-                          "sa_rounds_per_subject": st["sa_rounds"] / max(1, st["subjects"])},
-            "walk_ms_total": st["walk_ms"], "esa_ms_total": st["esa_ms"],
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "full_matrix": full_matrix,
+            "esa_build": {"mbp_per_s": ln / 1e6 / (esa_ms * 1e-3) if esa_ms > 0 else None, "ms_per_subject": esa_ms,
+                          "algorithmic_gbs": (esa_bytes / (esa_ms * 1e-3) / 1e9) if esa_ms > 0 else None,
+                          "sa_rounds_per_subject": st["sa_rounds"] / max(1, st["subjects"]),
+                          "timed": "alone (single lane); in the timed steps it overlaps the previous subject's walk"},
+            "kernel_ms_sums_of_timed_steps": {"walk": st["walk_ms"], "esa": st["esa_ms"], "rows_wall": st["rows_ms"]},
         }
         print(json.dumps(line))
     ctx.close()
@@ -425,6 +501,16 @@ def main():
         dist.destroy_process_group()
     if parity and parity["mismatches"]:
         raise SystemExit(f"bench.py: the benched workload differs from the {parity['against']} in {parity['mismatches']} cells")
+
+
+def kernel_sources_sha():
+    """Digest of the kernel sources: ties a profile capture to the code it was taken from."""
+    import hashlib
+
+    h = hashlib.sha1()
+    for f in sorted((ROOT / "andi_b200" / "csrc").glob("*.cu*")) + sorted((ROOT / "andi_b200" / "csrc").glob("*.h")):
+        h.update(f.read_bytes())
+    return h.hexdigest()[:12]
 
 
 if __name__ == "__main__":

@@ -174,6 +174,8 @@ typedef struct andi_stats {
 	uint64_t sa_rounds; /* prefix-doubling refinement rounds, summed over subjects */
 	uint64_t h2d_bytes, d2h_bytes;
 	uint64_t p2p_bytes; /* packed pool planes received from another device (andi_pool_import) */
+	double rows_ms;		/* device wall time of the andi_dist_rows calls (esa_ms and walk_ms are per-kernel
+						 * sums and overlap when two subjects are in flight) */
 } andi_stats;
 int andi_get_stats(const andi_ctx *ctx, andi_stats *out);
 void andi_reset_stats(andi_ctx *ctx);

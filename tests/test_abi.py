@@ -45,3 +45,15 @@ def test_product_never_imports_the_oracle():
             text = path.read_text()
             assert "import oracle" not in text and "from oracle" not in text, path
             assert "andi_oracle" not in text and "orc_" not in text, path
+
+
+def test_library_exports_the_reference_named_symbols():
+    """include/andi_compat.h: the reference's own C surface (src/esa.h:61-64, src/process.c:141,
+    src/process.h:11, src/dist_hack.h:34) -- what a relinked reference program binds."""
+    L = native.load()
+    header = (ROOT / "include" / "andi_compat.h").read_text()
+    declared = set(re.findall(r"^\w[\w \*]*?\b(\w+)\s*\([^;{]*\);", header, flags=re.M))
+    assert {"esa_init", "esa_free", "get_match", "get_match_cached", "dist_anchor", "distMatrix", "distMatrixLM",
+            "calculate_distances", "andi_compat_set_model"} <= declared, declared
+    for name in declared:
+        assert hasattr(L, name), name

@@ -47,3 +47,40 @@ def test_two_rank_gather_reassembles_the_matrix():
     ok = mp.get_context("spawn").Array("i", [0, 0])
     mp.spawn(_worker, args=(2, port, seqs, want, ok), nprocs=2, join=True)
     assert list(ok) == [1, 1]
+
+
+class _FakeCtx:
+    """Stands in for native.Context in the queue test: records which rows it was asked for."""
+
+    def __init__(self):
+        self.calls = []
+
+    def dist_rows_device(self, ptr, b, e, p_value, model):
+        self.calls.append((ptr, b, e))
+
+
+def _queue_worker(rank, world, port, n, batch, out):
+    store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0))
+    ctx = _FakeCtx()
+    done = driver.dynamic_rows(ctx, n, 1 << 20, lambda b: store.add("next", b) - b, batch)
+    assert done == sum(e - b for _, b, e in ctx.calls)
+    for ptr, b, e in ctx.calls:
+        assert ptr == (1 << 20) + b * n * 68  # row b of the full matrix, 68 bytes per cell
+        for r in range(b, e):
+            out[r] += 1
+    store.add("finished", 1)
+    while store.add("finished", 0) < world:  # rank 0 hosts the store: keep it alive until all are done
+        pass
+
+
+def test_dynamic_queue_hands_every_subject_to_exactly_one_rank():
+    """bench.py's whole-matrix leg: subjects are taken in batches from a shared counter
+    (TCPStore.add is an atomic fetch-and-add across ranks)."""
+    n, batch, world = 109, 4, 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = mp.get_context("spawn").Array("i", [0] * n)
+    mp.spawn(_queue_worker, args=(world, port, n, batch, out), nprocs=world, join=True)
+    assert list(out) == [1] * n

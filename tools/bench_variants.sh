@@ -6,7 +6,7 @@ out=gpurun_out/variants_${tag}.jsonl
 : > $out
 for lib in andi_b200/libandi_b200.so andi_b200/variants/libandi_b200_*.so; do
 	name=$(basename $lib .so)
-	line=$(ANDI_B200_LIB=$PWD/$lib python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e 2>/dev/null | tail -1)
+	line=$(ANDI_B200_LIB=$PWD/$lib python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e --no-full 2>/dev/null | tail -1)
 	echo "{\"variant\": \"$name\", \"line\": $line}" >> $out
 	python - "$name" "$line" <<'PY'
 import json, sys
