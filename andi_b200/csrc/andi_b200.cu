@@ -9,7 +9,7 @@
 #include "pack_tma.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include <cub/device/device_scan.cuh>	// doubling fallback (repeat-rich texts) only
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
@@ -46,10 +46,12 @@ struct andi_ctx {
 	// index-build scratch, grown on demand and reused for every subject (no allocation in the
 	// steady state of andi_dist_rows)
 	struct {
-		u32 *hist = nullptr, *bstart = nullptr, *grp = nullptr, *rank = nullptr, *flags = nullptr;
+		// hist has four zero entries in front (hist_alloc): hist - 1 is then the array of bucket starts
+		// once the scatter has turned hist into the array of bucket ends
+		u32 *hist_alloc = nullptr, *hist = nullptr, *bstart = nullptr, *grp = nullptr, *rank = nullptr, *flags = nullptr;
 		unsigned char *amb = nullptr;
-		void *scan_tmp = nullptr;
-		size_t scan_bytes = 0, kmers_cap = 0, n_cap = 0;
+		unsigned long long *scan_state = nullptr;  // k_scan_buckets: one word per tile + the ticket counter
+		size_t kmers_cap = 0, n_cap = 0;
 		// padded-suffix list of texts with separators (sa_bucket.cuh), double-buffered for the sort
 		u64 *pl_key[2] = {nullptr, nullptr};
 		u32 *pl_idx[2] = {nullptr, nullptr};
@@ -230,12 +232,12 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	harvest_events(ctx);
 	pool_release(ctx);
-	dfree(ctx, ctx->bs.hist), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
+	dfree(ctx, ctx->bs.hist_alloc), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
+	dfree(ctx, ctx->bs.scan_state);
 	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter);
 	dfree(ctx, ctx->bs.pl_key[0]), dfree(ctx, ctx->bs.pl_key[1]), dfree(ctx, ctx->bs.pl_idx[0]), dfree(ctx, ctx->bs.pl_idx[1]);
 	dfree(ctx, ctx->bs.fvalid);
 	if (ctx->bs.pl_tmp) cudaFreeAsync(ctx->bs.pl_tmp, ctx->stream);
-	if (ctx->bs.scan_tmp) cudaFreeAsync(ctx->bs.scan_tmp, ctx->stream);
 	cudaStreamSynchronize(ctx->stream);
 	for (auto e : ctx->free_ev) cudaEventDestroy(e);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -193,7 +193,7 @@ extern "C" int emu_v3_stats(void) { return ST_N; }
 extern "C" long emu_walk_v3(const u64 *s_code, u32 N, u32 mid, const u32 *SA, const u64 *fdir, int K, u32 self, u32 threshold,
 							const u64 *pool_code, const u64 *q_word_off, const u32 *q_len, u32 nq, u32 chunk, u32 cpq,
 							u32 *records, u64 *stats, u32 n_warps) {
-	if (!s_code || !SA || !fdir || !pool_code || !records || threshold > V3_MAX_T || K > (int)threshold || n_warps == 0) return -1;
+	if (!s_code || !SA || !fdir || !pool_code || !records || threshold > V3_MAX_T || K > (int)threshold || (int)threshold > K + 15 || n_warps == 0) return -1;
 	V3Const c;
 	c.t = threshold, c.N = N, c.mid = mid, c.border = N / 2, c.chunk = chunk, c.cpq = cpq, c.K = K, c.s_code = s_code, c.fdir = fdir;
 	Env env;

@@ -262,13 +262,12 @@ static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
 	auto &b = ctx->bs;
 	if (!b.flags) CK(dalloc(ctx, &b.flags, 4));
 	if (kmers > b.kmers_cap) {
-		dfree(ctx, b.hist), dfree(ctx, b.bstart);
-		if (b.scan_tmp) cudaFreeAsync(b.scan_tmp, ctx->stream);
-		CK(dalloc(ctx, &b.hist, kmers + 1));
+		dfree(ctx, b.hist_alloc), dfree(ctx, b.bstart), dfree(ctx, b.scan_state);
+		CK(dalloc(ctx, &b.hist_alloc, kmers + 1 + 4));
+		CK(cudaMemsetAsync(b.hist_alloc, 0, 4 * sizeof(u32), ctx->stream));
+		b.hist = b.hist_alloc + 4;
 		CK(dalloc(ctx, &b.bstart, kmers + 1));
-		b.scan_bytes = 0;
-		cub::DeviceScan::ExclusiveSum(nullptr, b.scan_bytes, b.hist, b.bstart, (int)(kmers + 1), ctx->stream);
-		CK(cudaMallocAsync(&b.scan_tmp, b.scan_bytes, ctx->stream));
+		CK(dalloc(ctx, &b.scan_state, (kmers + 1) / ANDI_SCAN_TILE + 2));
 		b.kmers_cap = kmers;
 	}
 	if (N > b.n_cap) {
@@ -278,6 +277,16 @@ static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
 		CK(dalloc(ctx, &b.amb, N));
 		b.n_cap = N;
 	}
+	return ANDI_OK;
+}
+
+// Exclusive prefix sums of hist[0, n) into out[0, n] (out may be hist), see k_scan_buckets.
+static int scan_buckets(andi_ctx *ctx, const u32 *hist, size_t n, u32 *out, u64 *dir64) {
+	auto &b = ctx->bs;
+	const unsigned tiles = nblocks(n + 1, ANDI_SCAN_TILE);
+	CK(cudaMemsetAsync(b.scan_state, 0, ((size_t)tiles + 1) * sizeof(unsigned long long), ctx->stream));
+	k_scan_buckets<<<tiles, 256, 0, ctx->stream>>>(hist, (u32)n, out, dir64, b.scan_state, reinterpret_cast<u32 *>(b.scan_state + tiles));
+	ctx->st.esa_launches++;
 	return ANDI_OK;
 }
 
@@ -313,8 +322,9 @@ static int padded_finish(andi_ctx *ctx, andi_esa *E, const TextView &rs) {
 	return ANDI_OK;
 }
 
-// Texts above this many characters bucket through the library radix sort (tables beyond L2).
-#define ANDI_BUCKET_ATOMIC_MAX (8u << 20)
+// Directories up to this many k-mers (K <= 12: a 64 MB histogram) are bucketed by counting sort
+// with atomics on L2-resident tables; deeper ones (texts of hundreds of Mbp) go through a radix sort.
+#define ANDI_BUCKET_ATOMIC_KMERS ((size_t)1 << 24)
 
 static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 	const u32 N = E->N;
@@ -338,26 +348,29 @@ rebuild:
 		CK(cudaMemsetAsync(b.pl_key[0], 0xff, b.pl_cap * sizeof(u64), st));
 		CK(cudaMemsetAsync(b.pl_idx[0], 0xff, b.pl_cap * sizeof(u32), st));
 	}
-	if (N <= ANDI_BUCKET_ATOMIC_MAX) {
+	const bool atomic_path = kmers <= ANDI_BUCKET_ATOMIC_KMERS;
+	const bool slots = atomic_path && !sep;	 // k_bucket_sort_slots: no bucket tables, one thread per suffix-array slot
+	if (atomic_path) {
 		// counting sort with L2-resident tables: histogram, scan, scatter
 		CK(cudaMemsetAsync(b.hist, 0, (kmers + 1) * sizeof(u32), st));
 		k_bucket_hist<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist);
-		size_t sb = b.scan_bytes;
-		CK(cub::DeviceScan::ExclusiveSum(b.scan_tmp, sb, b.hist, b.bstart, (int)(kmers + 1), st));
 		if (!sep) {
-			// the histogram becomes the scatter cursor: after the scatter hist[key] = end of bucket key
-			CK(cudaMemcpyAsync(b.hist, b.bstart, kmers * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+			// the histogram becomes the scatter cursor in place (and the scan writes the directory entries of
+			// the empty buckets); after the scatter hist[key] = end of bucket key, hist[key - 1] its start
+			rc = scan_buckets(ctx, b.hist, kmers, b.hist, E->dir);
+			if (rc) return rc;
 			k_bucket_scatter<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist, E->SA);
 			bend = b.hist;
 		} else {
 			// valid suffixes fill their bucket from the back: the cursor starts at the bucket end and
 			// stops at the first valid one; the padded ones go through the list to the front
+			rc = scan_buckets(ctx, b.hist, kmers, b.bstart, nullptr);
+			if (rc) return rc;
 			CK(cudaMemcpyAsync(b.hist, b.bstart + 1, kmers * sizeof(u32), cudaMemcpyDeviceToDevice, st));
 			k_bucket_scatter_spec<<<nblocks(N, 256), 256, 0, st>>>(rs, K, b.hist, E->SA, pl);
 			bend = b.bstart + 1, fvalid = b.hist;
 		}
 		ctx->st.esa_launches += 2;
-		ctx->st.cub_calls += 1;
 	} else {
 		// (key, position) pairs through the library radix sort, bounds from the sorted keys
 		u32 *keys_a = nullptr, *keys_b = nullptr, *idx = nullptr;
@@ -400,10 +413,13 @@ rebuild:
 	if (sep) {
 		rc = padded_finish(ctx, E, rs);
 		if (rc) return rc;
-		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, N <= ANDI_BUCKET_ATOMIC_MAX, present_top);
+		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, atomic_path, present_top);
 		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	} else {
-		k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, E->dir, b.flags, N <= ANDI_BUCKET_ATOMIC_MAX, present_top);
+		if (slots)
+			k_bucket_sort_slots<<<nblocks(N, 128), 128, 0, st>>>(rs, K, E->SA, E->dir, b.flags, present_top);
+		else
+			k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, E->dir, b.flags, atomic_path, present_top);
 		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	}
 	ctx->st.esa_launches += 2;

@@ -224,13 +224,16 @@ __global__ void k_padded_place(int K, const u64 *__restrict__ key, const u32 *__
 // separator inside) | their number << 32; first + number = end of the bucket. *n_ambiguous counts the suffixes that are still tied
 // with a neighbour; their groups are materialised by k_bucket_groups only when there are any.
 template <bool SPEC>
+__device__ __forceinline__ u32 bucket_sort_range(const TextView &rs, int K, u32 key, u32 b, u32 e, bool presorted_front,
+												 u32 *__restrict__ SA, u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous);
+
+// One bucket, found through the tables of the bucketing pass: [bstart[key], bend[key]).
+template <bool SPEC>
 __device__ __forceinline__ u32 bucket_sort_key(const TextView &rs, int K, u32 key, const u32 *__restrict__ bstart,
 											   const u32 *__restrict__ bend, const u32 *__restrict__ fvalid,
 											   u32 *__restrict__ SA, u64 *__restrict__ dir64,
 											   u32 *__restrict__ n_ambiguous, u32 empty_known) {
 	const u32 e = bend[key];
-	// fvalid given: the padded suffixes already stand sorted in [bstart, fvalid) (k_padded_place)
-	const u32 b = fvalid ? min(fvalid[key], e) : bstart[key], s = e - b;
 	if (e == bstart[key]) {
 		// first + count is the END of the bucket for every key, so the start of bucket k is the
 		// end of k-1 (the generic search narrows its range with that). The radix bucketing path
@@ -238,6 +241,16 @@ __device__ __forceinline__ u32 bucket_sort_key(const TextView &rs, int K, u32 ke
 		dir64[key] = empty_known ? (u64)e : 0xffffffffULL;
 		return 0;
 	}
+	// fvalid given: the padded suffixes already stand sorted in [bstart, fvalid) (k_padded_place)
+	return bucket_sort_range<SPEC>(rs, K, key, fvalid ? min(fvalid[key], e) : bstart[key], e, fvalid != nullptr, SA, dir64, n_ambiguous);
+}
+
+// Order the suffixes SA[b, e) of one bucket (b < e unless presorted_front) and emit its directory entry.
+template <bool SPEC>
+__device__ __forceinline__ u32 bucket_sort_range(const TextView &rs, int K, u32 key, u32 b, u32 e, bool presorted_front,
+												 u32 *__restrict__ SA, u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous) {
+	const bool fvalid = presorted_front;
+	const u32 s = e - b;
 	if (fvalid && s > ANDI_SORT_MAX) {	// valid suffixes only: one group of depth K for the doubling rounds
 		atomicAdd(n_ambiguous, s);
 		dir64[key] = (u64)b | ((u64)s << 32);
@@ -336,6 +349,113 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 	}
 }
 
+
+
+// ---- k_bucket_sort_slots (texts without separators): the same per-bucket work with one thread per
+// suffix-array SLOT instead of one per k-mer. At depth K = log4(N) + 1 three buckets in four are
+// empty, and a thread per k-mer spends most of the kernel reading table entries of empty buckets
+// (18 % of the whole build in round 1). Here thread j looks at the suffix the bucketing pass left
+// in slot j and at its left neighbour: if their k-mers differ, j is the head of a bucket; it finds
+// the end of the bucket the same way and sorts it. No bucket table is read at all; the entries of
+// EMPTY buckets are written by the scan kernel below. Presence bits (level K-1) by atomicOr.
+__device__ __forceinline__ u32 padded_key_nosep(const TextView &rs, u32 p, int K) {
+	const u32 run = p <= rs.mid ? rs.mid - p : rs.len - p;	// nucleotides before '#' / the end
+	u64 cw = window32(rs.code, p);
+	if (run < 32u) cw &= (1ULL << (2u * run)) - 1ULL;
+	return kmer_key(cw, K);
+}
+
+__global__ void k_bucket_sort_slots(TextView rs, int K, u32 *__restrict__ SA, u64 *__restrict__ dir64,
+									u32 *__restrict__ n_ambiguous, u32 *__restrict__ present_top) {
+	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= rs.len) return;
+	const u32 key = padded_key_nosep(rs, SA[j], K);
+	if (j > 0 && padded_key_nosep(rs, SA[j - 1], K) == key) return;	 // not the head of its bucket
+	u32 e = j + 1;
+	while (e < rs.len && padded_key_nosep(rs, SA[e], K) == key) e++;
+	const u32 count = bucket_sort_range<false>(rs, K, key, j, e, false, SA, dir64, n_ambiguous);
+	if (count) {
+		const u32 y = key >> 2;	 // its (K-1)-mer
+		atomicOr(present_top + (y >> 5), 1u << (y & 31u));
+	}
+}
+
+// ---- k_scan_buckets: exclusive prefix sums over the k-mer histogram in ONE pass (decoupled
+// look-back over tiles of ANDI_SCAN_TILE keys; stands where round 1 called cub::DeviceScan).
+// out[k] = number of suffixes in buckets < k (may alias hist: the histogram becomes the scatter
+// cursor), out[n] = N. With dir64 given, the directory entries of EMPTY buckets are written on
+// the way (first = end of the bucket, count 0): k_bucket_sort_slots never sees those buckets.
+#define ANDI_SCAN_TILE 4096u  // 256 threads x 16 keys
+__global__ void __launch_bounds__(256) k_scan_buckets(const u32 *hist, u32 n, u32 *out, u64 *__restrict__ dir64,
+													  unsigned long long *tile_state, u32 *tile_ticket) {
+	__shared__ u32 warp_sum[8];
+	__shared__ u32 s_tile, s_prefix;
+	if (threadIdx.x == 0) s_tile = atomicAdd(tile_ticket, 1u);	// tiles start in ticket order: no deadlock
+	__syncthreads();
+	const u32 tile = s_tile, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	const u32 base = tile * ANDI_SCAN_TILE + threadIdx.x * 16u;
+	u32 v[16];
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		uint4 x = make_uint4(0, 0, 0, 0);
+		if (base + 4u * q + 3u < n)
+			x = *reinterpret_cast<const uint4 *>(hist + base + 4u * q);
+		else {
+			if (base + 4u * q + 0u < n) x.x = hist[base + 4u * q + 0u];
+			if (base + 4u * q + 1u < n) x.y = hist[base + 4u * q + 1u];
+			if (base + 4u * q + 2u < n) x.z = hist[base + 4u * q + 2u];
+		}
+		v[4 * q] = x.x, v[4 * q + 1] = x.y, v[4 * q + 2] = x.z, v[4 * q + 3] = x.w;
+	}
+	u32 mine = 0;
+#pragma unroll
+	for (int q = 0; q < 16; q++) mine += v[q];
+	u32 inc = mine;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= (u32)d) inc += y;
+	}
+	if (lane == 31u) warp_sum[wid] = inc;
+	__syncthreads();
+	u32 before = 0, total = 0;
+#pragma unroll
+	for (u32 k = 0; k < 8; k++) {
+		const u32 ws = warp_sum[k];
+		before += k < wid ? ws : 0u;
+		total += ws;
+	}
+	// tile_state[t] = value | status << 62: 1 = the tile's own sum, 2 = sum of all tiles up to and including t
+	if (threadIdx.x == 0) {
+		volatile unsigned long long *st = tile_state;
+		if (tile == 0) {
+			st[0] = (2ULL << 62) | total;
+			s_prefix = 0;
+		} else {
+			st[tile] = (1ULL << 62) | total;
+			u32 prefix = 0;
+			for (u32 t = tile; t-- > 0;) {
+				unsigned long long x;
+				do x = st[t];
+				while ((x >> 62) == 0ULL);
+				prefix += (u32)x;
+				if ((x >> 62) == 2ULL) break;
+			}
+			st[tile] = (2ULL << 62) | (unsigned long long)(prefix + total);
+			s_prefix = prefix;
+		}
+	}
+	__syncthreads();
+	u32 run = s_prefix + before + inc - mine;
+	const u32 end = n;	// out has n + 1 entries
+#pragma unroll
+	for (int q = 0; q < 16; q++) {
+		const u32 k = base + (u32)q;
+		if (k <= end) out[k] = run;	 // v is zero from n on, so out[n] = N
+		if (dir64 && k < end && v[q] == 0u) dir64[k] = (u64)run;
+		run += v[q];
+	}
+}
 
 // The walk's view of the directory, one 8-byte entry per k-mer so that the common lookups cost
 // ONE table access (the tables compete with the streaming queries for L2):

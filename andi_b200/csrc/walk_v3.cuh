@@ -122,6 +122,7 @@ k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32
 }
 
 // Can this walk go through k_walk_v3? (else: k_walk_chunks_fast)
+// (threshold <= K + 15: a tag-1 directory entry must be able to prove a match of threshold length)
 static inline bool v3_applies(const SubjectIndex &S, u32 threshold) {
-	return S.K > 0 && threshold <= V3_MAX_T && (u32)S.K <= threshold && S.fdir != nullptr;
+	return S.K > 0 && threshold <= V3_MAX_T && (u32)S.K <= threshold && threshold <= (u32)S.K + 15u && S.fdir != nullptr;
 }
