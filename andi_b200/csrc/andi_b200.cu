@@ -63,6 +63,10 @@ struct andi_ctx {
 
 	unsigned long long *walk_counter = nullptr;  // unit dispenser of the walk kernels
 
+	// pinned staging planes of andi_pool_set_host (the pool is packed on the host, host_pack.c)
+	u64 *h_code = nullptr, *h_spec = nullptr;
+	size_t h_words = 0;
+
 	// Second lane of andi_dist_rows: a helper context on its own stream that BORROWS this pool, so
 	// that the index build and the walk of subject i+1 fill the tail of subject i's walk
 	// (walk_host.cuh). Created on first use, destroyed with its owner.
@@ -227,6 +231,8 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 		andi_ctx_destroy(ctx->helper);
 		ctx->helper = nullptr;
 	}
+	if (ctx->h_code) cudaFreeHost(ctx->h_code);
+	if (ctx->h_spec) cudaFreeHost(ctx->h_spec);
 	if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
 	if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
 	cudaStreamSynchronize(ctx->stream);
@@ -371,6 +377,72 @@ static int pool_check(andi_ctx *ctx, const size_t *lens, size_t n) {
 	return ANDI_OK;
 }
 
+extern "C" {
+void andi_host_pack_pool(const char *const *seqs, const size_t *lens, const size_t *word_off, const size_t *nwords, size_t k0, size_t k1,
+						 uint64_t *code, uint64_t *spec, uint64_t *gc, uint64_t *sep);
+}
+
+// The pool from host memory. The characters are packed to 2 bits per base ON THE HOST (host_pack.c:
+// AVX2, all cores) into pinned staging planes and uploaded packed, chunk by chunk, so that packing
+// chunk c + 1 overlaps the upload of chunk c: a quarter of the bytes on PCIe. ANDI_B200_HOST_PACK=0
+// uploads the characters and packs on the device instead (k_pack_tma, what andi_pool_set_device does).
+static int pool_set_host_packed(andi_ctx *ctx, const char *const *seqs, const size_t *lens, size_t n) {
+	std::vector<size_t> nwords(n);
+	size_t words = 0;
+	ctx->word_off.resize(n);
+	for (size_t k = 0; k < n; k++) {
+		ctx->word_off[k] = words;
+		nwords[k] = plane_words(lens[k]);
+		words += (nwords[k] + 1) & ~(size_t)1;	// keep 16-byte alignment
+	}
+	if (words > ctx->h_words) {
+		if (ctx->h_code) cudaFreeHost(ctx->h_code);
+		if (ctx->h_spec) cudaFreeHost(ctx->h_spec);
+		ctx->h_code = ctx->h_spec = nullptr, ctx->h_words = 0;
+		CK(cudaHostAlloc((void **)&ctx->h_code, words * sizeof(u64), cudaHostAllocDefault));
+		CK(cudaHostAlloc((void **)&ctx->h_spec, words * sizeof(u64), cudaHostAllocDefault));
+		ctx->h_words = words;
+	}
+	CK(dalloc(ctx, &ctx->pool_code, words));
+	CK(dalloc(ctx, &ctx->pool_spec, words));
+	ctx->pool_words = words;
+	std::vector<uint64_t> gc(n), sep(n);
+	const size_t chunk_chars = (size_t)256 << 20;
+	for (size_t k0 = 0; k0 < n;) {
+		size_t k1 = k0, chars = 0;
+		while (k1 < n && (k1 == k0 || chars + lens[k1] <= chunk_chars)) chars += lens[k1++];
+		andi_host_pack_pool(seqs, lens, ctx->word_off.data(), nwords.data(), k0, k1, reinterpret_cast<uint64_t *>(ctx->h_code), reinterpret_cast<uint64_t *>(ctx->h_spec), gc.data(), sep.data());
+		bool any = false;
+		for (size_t k = k0; k < k1; k++) {
+			any |= sep[k] != 0;
+			if (nwords[k] & 1) ctx->h_code[ctx->word_off[k] + nwords[k]] = 0, ctx->h_spec[ctx->word_off[k] + nwords[k]] = 0;	// alignment pad
+		}
+		const size_t w0 = ctx->word_off[k0], w1 = k1 < n ? ctx->word_off[k1] : words;
+		CK(cudaMemcpyAsync(ctx->pool_code + w0, ctx->h_code + w0, (w1 - w0) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+		ctx->st.h2d_bytes += (w1 - w0) * sizeof(u64);
+		if (any) {
+			CK(cudaMemcpyAsync(ctx->pool_spec + w0, ctx->h_spec + w0, (w1 - w0) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+			ctx->st.h2d_bytes += (w1 - w0) * sizeof(u64);
+		} else {
+			CK(cudaMemsetAsync(ctx->pool_spec + w0, 0, (w1 - w0) * sizeof(u64), ctx->stream));
+		}
+		k0 = k1;
+	}
+	ctx->gc.resize(n), ctx->has_sep.resize(n);
+	std::vector<QueryView> qv(n);
+	for (size_t k = 0; k < n; k++) {
+		ctx->gc[k] = (double)gc[k] / (double)lens[k];  // src/sequence.c:196-207
+		ctx->has_sep[k] = sep[k] != 0;
+		ctx->any_sep |= ctx->has_sep[k] != 0;
+		qv[k].t.code = ctx->pool_code + ctx->word_off[k], qv[k].t.spec = ctx->pool_spec + ctx->word_off[k];
+		qv[k].t.len = (u32)lens[k], qv[k].t.mid = 0xffffffffu, qv[k].has_sep = ctx->has_sep[k];
+	}
+	CK(dalloc(ctx, &ctx->d_queries, n));
+	CK(cudaMemcpyAsync(ctx->d_queries, qv.data(), n * sizeof(QueryView), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ANDI_OK;
+}
+
 extern "C" int andi_pool_set_host(andi_ctx *ctx, const char *const *seqs, const size_t *lens, size_t n) {
 	if (!ctx || !seqs) return ANDI_ERR_ARG;
 	int rc = pool_check(ctx, lens, n);
@@ -379,6 +451,12 @@ extern "C" int andi_pool_set_host(andi_ctx *ctx, const char *const *seqs, const 
 	pool_release(ctx);
 	ctx->n = n;
 	ctx->len.assign(lens, lens + n);
+	const char *hp = getenv("ANDI_B200_HOST_PACK");
+	if (!(hp && atoi(hp) == 0)) {
+		rc = pool_set_host_packed(ctx, seqs, lens, n);
+		if (rc) pool_release(ctx);
+		return rc;
+	}
 	std::vector<size_t> offs(n);
 	size_t total = 0;
 	for (size_t k = 0; k < n; k++) {
@@ -392,6 +470,7 @@ extern "C" int andi_pool_set_host(andi_ctx *ctx, const char *const *seqs, const 
 	ctx->st.h2d_bytes += total;
 	rc = pool_finish(ctx, d_chars, offs);
 	dfree(ctx, d_chars);
+	if (rc) pool_release(ctx);
 	return rc;
 }
 
@@ -405,7 +484,9 @@ extern "C" int andi_pool_set_device(andi_ctx *ctx, const char *d_chars, const si
 	ctx->n = n;
 	ctx->len.assign(lens, lens + n);
 	std::vector<size_t> offs(offsets, offsets + n);
-	return pool_finish(ctx, (const unsigned char *)d_chars, offs);
+	rc = pool_finish(ctx, (const unsigned char *)d_chars, offs);
+	if (rc) pool_release(ctx);	// no half-set pool
+	return rc;
 }
 
 extern "C" size_t andi_pool_size(const andi_ctx *ctx) { return ctx ? ctx->n : 0; }
@@ -518,9 +599,10 @@ extern "C" int andi_esa_build_rs(andi_ctx *ctx, const char *rs, size_t rs_len, u
 		delete E;
 		return ANDI_ERR_CUDA;
 	}
-	// A general RS string may hold '#' anywhere (or not at all); the SPEC path makes no
-	// assumption about it, so use it unless the string has the canonical shape.
-	E->has_sep = cnt[1] != 0 || (rs_len % 2 == 0) || rs[rs_len / 2] != '#';
+	// A general RS string may hold '#' anywhere, several times or not at all; the SPEC path makes
+	// no assumption about it, so use it unless the string has the canonical shape: no other
+	// separator and exactly ONE '#', in the middle (the non-SPEC kernels know '#' by position only).
+	E->has_sep = cnt[1] != 0 || cnt[0] != 1 || (rs_len % 2 == 0) || rs[rs_len / 2] != '#';
 	// gc of the forward half for the default threshold
 	size_t gcn = 0;
 	for (size_t k = E->n + 1; k < rs_len; k++) gcn += (rs[k] == 'G' || rs[k] == 'C');
@@ -698,6 +780,13 @@ extern "C" int andi_esa_get_match(const andi_esa *E, const char *const *queries,
 	CK(cudaStreamSynchronize(ctx->stream));
 	dfree(ctx, d_out);
 	temp_release(ctx, T);
+	// l == -2 is k_get_match's mark for "the directory lookup and the full-range search disagree":
+	// an internal error, never an answer
+	for (size_t k = 0; k < nq; k++)
+		if (out[k].l == -2) {
+			ctx->err = "get_match: directory lookup and generic search disagree (internal error)";
+			return ANDI_ERR_CUDA;
+		}
 	return ANDI_OK;
 }
 

@@ -52,13 +52,13 @@ __global__ void k_pack(const unsigned char *__restrict__ chars, u32 n, u64 *__re
 }
 
 // Pack an RS string given as bytes (andi_esa_build_rs): same coding, '#' -> (spec, 1),
-// ';' -> (spec, 2), '!' -> (spec, 0).
+// ';' -> (spec, 2), '!' -> (spec, 0). counters[0] += number of '#', counters[1] += other separators.
 __global__ void k_pack_rs_bytes(const unsigned char *__restrict__ chars, u32 n, u64 *__restrict__ code,
 								u64 *__restrict__ spec, u32 nwords, unsigned long long *counters) {
 	u32 w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= nwords) return;
 	u64 cw = 0, sw = 0;
-	u32 base = w * 32u, sep = 0;
+	u32 base = w * 32u, sep = 0, hashes = 0;
 	if (base < n) {
 		u32 cnt = n - base < 32u ? n - base : 32u;
 		for (u32 d = 0; d < cnt; d++) {
@@ -70,6 +70,7 @@ __global__ void k_pack_rs_bytes(const unsigned char *__restrict__ chars, u32 n, 
 			if (!nuc) {
 				v = c == '#' ? 1u : c == ';' ? 2u : 0u;
 				sep += (c != '#');
+				hashes += (c == '#');
 			}
 			cw |= (u64)v << (2 * d);
 			sw |= (u64)(!nuc) << (2 * d);
@@ -78,6 +79,7 @@ __global__ void k_pack_rs_bytes(const unsigned char *__restrict__ chars, u32 n, 
 	code[w] = cw;
 	spec[w] = sw;
 	if (sep) atomicAdd(&counters[1], (unsigned long long)sep);
+	if (hashes) atomicAdd(&counters[0], (unsigned long long)hashes);  // counters[0] = number of '#'
 }
 
 // src/sequence.c:143-189 (revcomp + catcomp) on packed planes:

@@ -349,7 +349,8 @@ rebuild:
 		CK(cudaMemsetAsync(b.pl_idx[0], 0xff, b.pl_cap * sizeof(u32), st));
 	}
 	const bool atomic_path = kmers <= ANDI_BUCKET_ATOMIC_KMERS;
-	const bool slots = atomic_path && !sep;	 // k_bucket_sort_slots: no bucket tables, one thread per suffix-array slot
+	bool slots = atomic_path && !sep;  // k_bucket_sort_slots: no bucket tables, one thread per suffix-array slot
+	const bool key_sort = getenv("ANDI_B200_KEY_SORT") != nullptr;  // experiments: the one-thread-per-k-mer kernel on the same tables
 	if (atomic_path) {
 		// counting sort with L2-resident tables: histogram, scan, scatter
 		CK(cudaMemsetAsync(b.hist, 0, (kmers + 1) * sizeof(u32), st));
@@ -371,36 +372,54 @@ rebuild:
 			bend = b.bstart + 1, fvalid = b.hist;
 		}
 		ctx->st.esa_launches += 2;
+	} else if (!sep) {
+		// deep directory, no separators: own two-level counting sort (sa_bucket.cuh)
+		const int K2 = K / 2, K1 = K - K2;
+		const u32 parts = 1u << (2 * K1), bins = 1u << (2 * K2);
+		const unsigned ctas = (unsigned)ctx->sm_count * 2u;
+		const u32 per_cta = (N + ctas - 1) / ctas;
+		static bool attr_set = false;
+		if (!attr_set) {
+			CK(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+			CK(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+			CK(cudaFuncSetAttribute(k_part_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 128));
+			attr_set = true;
+		}
+		u32 *hist1 = b.bstart, *start1 = b.bstart + parts + 4;	 // level-1 tables live in the (unused) bucket-start scratch
+		CK(cudaMemsetAsync(hist1, 0, (parts + 1) * sizeof(u32), st));
+		k_part_hist<<<ctas, 1024, parts * sizeof(u32), st>>>(rs, K, K2, per_cta, hist1);
+		rc = scan_buckets(ctx, hist1, parts, start1, nullptr);
+		if (rc) return rc;
+		CK(cudaMemcpyAsync(hist1, start1, parts * sizeof(u32), cudaMemcpyDeviceToDevice, st));	// cursors
+		k_part_scatter<<<ctas, 1024, parts * sizeof(u32), st>>>(rs, K, K2, per_cta, hist1, b.grp);
+		k_part_sort<<<parts, 1024, bins * sizeof(u32) + 128, st>>>(rs, K, K2, start1, b.grp, E->SA, b.hist, E->dir);
+		bend = b.hist;	// bucket ends; hist - 1 = bucket starts (hist_alloc holds zeros in front)
+		slots = true;
+		ctx->st.esa_launches += 3;
 	} else {
-		// (key, position) pairs through the library radix sort, bounds from the sorted keys
+		// deep directory WITH separators (join mode on a genome of hundreds of Mbp): (key, position)
+		// pairs through the library radix sort, bounds from the sorted keys
 		u32 *keys_a = nullptr, *keys_b = nullptr, *idx = nullptr;
 		CK(dalloc(ctx, &keys_a, N));
 		CK(dalloc(ctx, &keys_b, N));
 		CK(dalloc(ctx, &idx, N));
-		const int bits = 2 * K + (sep ? 1 : 0);
+		const int bits = 2 * K + 1;
 		size_t sort_bytes = 0;
 		cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_a, keys_b, idx, E->SA, (int)N, 0, bits, st);
 		void *tmp = nullptr;
 		CK(cudaMallocAsync(&tmp, sort_bytes, st));
-		if (sep)
-			k_bucket_keys_spec<<<nblocks(N, 256), 256, 0, st>>>(rs, K, keys_a, idx, pl);
-		else
-			k_bucket_keys<<<nblocks(N, 256), 256, 0, st>>>(rs, K, keys_a, idx);
+		k_bucket_keys_spec<<<nblocks(N, 256), 256, 0, st>>>(rs, K, keys_a, idx, pl);
 		CK(cub::DeviceRadixSort::SortPairs(tmp, sort_bytes, keys_a, keys_b, idx, E->SA, (int)N, 0, bits, st));
 		CK(cudaMemsetAsync(b.bstart, 0, kmers * sizeof(u32), st));
 		CK(cudaMemsetAsync(b.hist, 0, kmers * sizeof(u32), st));
-		if (sep) {
-			if (kmers > b.fvalid_cap) {
-				dfree(ctx, b.fvalid);
-				CK(dalloc(ctx, &b.fvalid, kmers));
-				b.fvalid_cap = kmers;
-			}
-			CK(cudaMemsetAsync(b.fvalid, 0, kmers * sizeof(u32), st));
-			k_bucket_bounds_spec<<<nblocks(N, 256), 256, 0, st>>>(keys_b, N, b.bstart, b.hist, b.fvalid);
-			fvalid = b.fvalid;
-		} else {
-			k_bucket_bounds<<<nblocks(N, 256), 256, 0, st>>>(keys_b, N, b.bstart, b.hist);
+		if (kmers > b.fvalid_cap) {
+			dfree(ctx, b.fvalid);
+			CK(dalloc(ctx, &b.fvalid, kmers));
+			b.fvalid_cap = kmers;
 		}
+		CK(cudaMemsetAsync(b.fvalid, 0, kmers * sizeof(u32), st));
+		k_bucket_bounds_spec<<<nblocks(N, 256), 256, 0, st>>>(keys_b, N, b.bstart, b.hist, b.fvalid);
+		fvalid = b.fvalid;
 		bend = b.hist;
 		cudaFreeAsync(tmp, st);
 		dfree(ctx, keys_a), dfree(ctx, keys_b), dfree(ctx, idx);
@@ -416,10 +435,10 @@ rebuild:
 		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, atomic_path, present_top);
 		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	} else {
-		if (slots)
+		if (slots && !key_sort)
 			k_bucket_sort_slots<<<nblocks(N, 128), 128, 0, st>>>(rs, K, E->SA, E->dir, b.flags, present_top);
 		else
-			k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, E->dir, b.flags, atomic_path, present_top);
+			k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, slots ? b.hist - 1 : b.bstart, bend, nullptr, E->SA, E->dir, b.flags, atomic_path || slots, present_top);
 		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	}
 	ctx->st.esa_launches += 2;
@@ -444,7 +463,8 @@ rebuild:
 		if (E->has_sep)
 			k_bucket_groups<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, b.grp, b.rank, b.amb);
 		else
-			k_bucket_groups<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, nullptr, E->SA, b.grp, b.rank, b.amb);
+			// (slots: the scatter left the bucket ends in hist, so hist - 1 is the array of bucket starts)
+			k_bucket_groups<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, slots ? b.hist - 1 : b.bstart, bend, nullptr, E->SA, b.grp, b.rank, b.amb);
 		ctx->st.esa_launches++;
 		rc = doubling_rounds(ctx, E, b.grp, b.rank, b.amb, (u32)K);
 		if (!rc) {

@@ -457,6 +457,88 @@ __global__ void __launch_bounds__(256) k_scan_buckets(const u32 *hist, u32 n, u3
 	}
 }
 
+
+// ---- two-level counting sort for DEEP directories (K >= 13: texts of hundreds of Mbp, config 5).
+// A histogram of 4^K counters (1 GB at K = 14) is far beyond L2, and random atomics on it run at
+// DRAM-sector speed; round 1 went through cub::DeviceRadixSort there. Own replacement:
+//   level 1  partition all suffixes by their first K1 = ceil(K/2) bases (<= 16384 parts): every CTA
+//            histograms its stretch of the text in shared memory, reserves its share of every part
+//            with ONE global atomic per non-empty part, and scatters through shared-memory cursors
+//            (k_part_hist, k_scan_buckets, k_part_scatter) -> positions grouped by part in `tmp`
+//   level 2  one CTA per part: counting sort of its suffixes on the remaining K2 = K - K1 bases with
+//            a 4^K2-counter histogram in shared memory; it knows every bucket of its part, so it
+//            writes the bucket ends, and the directory entries of the empty buckets, as coalesced
+//            streams (k_part_sort) -> SA grouped by k-mer, exactly what the atomics path leaves
+// Texts without separators only. Traffic: the text twice (L2), 3 x 4N bytes of positions.
+__global__ void __launch_bounds__(1024) k_part_hist(TextView rs, int K, int K2, u32 per_cta, u32 *__restrict__ hist1) {
+	extern __shared__ u32 sh[];
+	const u32 parts = 1u << (2 * (K - K2));
+	for (u32 x = threadIdx.x; x < parts; x += blockDim.x) sh[x] = 0;
+	__syncthreads();
+	const u32 c0 = blockIdx.x * per_cta, c1 = min(rs.len, c0 + per_cta);
+	for (u32 i = c0 + threadIdx.x; i < c1; i += blockDim.x) atomicAdd(&sh[padded_key_nosep(rs, i, K) >> (2 * K2)], 1u);
+	__syncthreads();
+	for (u32 x = threadIdx.x; x < parts; x += blockDim.x)
+		if (sh[x]) atomicAdd(hist1 + x, sh[x]);
+}
+
+__global__ void __launch_bounds__(1024) k_part_scatter(TextView rs, int K, int K2, u32 per_cta, u32 *__restrict__ cursor1,
+														u32 *__restrict__ tmp) {
+	extern __shared__ u32 sh[];
+	const u32 parts = 1u << (2 * (K - K2));
+	for (u32 x = threadIdx.x; x < parts; x += blockDim.x) sh[x] = 0;
+	__syncthreads();
+	const u32 c0 = blockIdx.x * per_cta, c1 = min(rs.len, c0 + per_cta);
+	for (u32 i = c0 + threadIdx.x; i < c1; i += blockDim.x) atomicAdd(&sh[padded_key_nosep(rs, i, K) >> (2 * K2)], 1u);
+	__syncthreads();
+	for (u32 x = threadIdx.x; x < parts; x += blockDim.x)
+		if (sh[x]) sh[x] = atomicAdd(cursor1 + x, sh[x]);  // this CTA's slots of part x start here
+	__syncthreads();
+	for (u32 i = c0 + threadIdx.x; i < c1; i += blockDim.x) tmp[atomicAdd(&sh[padded_key_nosep(rs, i, K) >> (2 * K2)], 1u)] = i;
+}
+
+// start1[x] = first slot of part x (x = blockIdx.x), start1[x + 1] its end. bend[key] = end of bucket key.
+__global__ void __launch_bounds__(1024) k_part_sort(TextView rs, int K, int K2, const u32 *__restrict__ start1,
+													 const u32 *__restrict__ tmp, u32 *__restrict__ SA, u32 *__restrict__ bend,
+													 u64 *__restrict__ dir64) {
+	extern __shared__ u32 sh[];	 // 4^K2 counters, then 32 warp sums
+	const u32 bins = 1u << (2 * K2), mask = bins - 1u, part = blockIdx.x;
+	const u32 s = start1[part], e = start1[part + 1];
+	u32 *warp_sum = sh + bins;
+	for (u32 x = threadIdx.x; x < bins; x += blockDim.x) sh[x] = 0;
+	__syncthreads();
+	for (u32 j = s + threadIdx.x; j < e; j += blockDim.x) atomicAdd(&sh[padded_key_nosep(rs, tmp[j], K) & mask], 1u);
+	__syncthreads();
+	// exclusive scan of the counters: every thread owns bins / 1024 consecutive ones (4 or 16)
+	const u32 per = bins / blockDim.x, b0 = threadIdx.x * per, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	u32 mine = 0;
+	for (u32 x = 0; x < per; x++) mine += sh[b0 + x];
+	u32 inc = mine;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= (u32)d) inc += y;
+	}
+	if (lane == 31u) warp_sum[wid] = inc;
+	__syncthreads();
+	u32 before = 0;
+	for (u32 k = 0; k < wid; k++) before += warp_sum[k];
+	u32 run = s + before + inc - mine;
+	const size_t key0 = ((size_t)part << (2 * K2)) + b0;
+	for (u32 x = 0; x < per; x++) {
+		const u32 cnt = sh[b0 + x];
+		if (cnt == 0) dir64[key0 + x] = (u64)run;  // empty bucket: first = its end, count 0
+		sh[b0 + x] = run;						   // cursor
+		run += cnt;
+		bend[key0 + x] = run;
+	}
+	__syncthreads();
+	for (u32 j = s + threadIdx.x; j < e; j += blockDim.x) {
+		const u32 i = tmp[j];
+		SA[atomicAdd(&sh[padded_key_nosep(rs, i, K) & mask], 1u)] = i;
+	}
+}
+
 // The walk's view of the directory, one 8-byte entry per k-mer so that the common lookups cost
 // ONE table access (the tables compete with the streaming queries for L2):
 //   tag 0 (absent k-mer)    low bits = plen: the longest prefix of the k-mer present in RS, which

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from pathlib import Path
 
 import numpy as np
@@ -123,6 +124,7 @@ class Esa:
     def __init__(self, ctx: "Context", handle):
         self.ctx, self.h = ctx, handle
         self.N = int(load().andi_esa_len(handle))
+        ctx._esas.add(self)  # the context frees its live indexes before it goes (andi_esa_free needs the context)
 
     def download(self, full: bool = False) -> dict:
         N = self.N
@@ -146,9 +148,9 @@ class Esa:
         return np.frombuffer(out, dtype=np.int32).reshape(n, 4).copy()
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:
             load().andi_esa_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -168,6 +170,7 @@ class Context:
             raise AndiError(f"andi_ctx_create: {ERRORS.get(rc, rc)}: {L.andi_last_error(None).decode()}")
         self.h = h
         self._keep = None
+        self._esas = weakref.WeakSet()
 
     def _ck(self, rc: int):
         if rc:
@@ -266,6 +269,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for e in list(self._esas):  # andi_esa_free uses the context's device and stream
+                e.free()
             load().andi_ctx_destroy(self.h)
             self.h = None
 

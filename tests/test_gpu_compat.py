@@ -118,3 +118,24 @@ def test_dist_anchor_like_dist_hack(lib, model):
                 assert list(m.counts) + [m.seq_len] == want[i, j].tolist(), (name, i, j)
             lib.esa_free(C.byref(E))
     lib.andi_compat_set_model(oracle.MODELS["JC"])
+
+
+def test_rs_string_with_a_stray_separator():
+    """andi_esa_build_rs takes ANY RS string (the compat esa_init hands it seq_subject.RS): a second
+    '#' away from the middle must not be read as a nucleotide (it selects the separator-aware
+    kernels). Checked against a plain sort of the suffixes in the reference's byte order."""
+    import numpy as np
+
+    from andi_b200 import native, synth
+
+    half = synth.ACGT[synth.base_genome(700, 3)].tobytes()
+    # odd length 1401 with '#' in the middle (index 700) -- the canonical shape -- plus a second '#' at 200
+    rs = half[:200] + b"#" + half[200:699] + b"#" + half[::-1]
+    assert len(rs) == 1401 and rs[700:701] == b"#" and rs.count(b"#") == 2
+    ctx = native.Context(0)
+    e = ctx.esa_build_rs(rs)
+    got = e.download()["SA"]
+    want = np.array(sorted(range(len(rs)), key=lambda i: rs[i:]), dtype=np.int32)
+    assert np.array_equal(got, want)
+    e.free()
+    ctx.close()
