@@ -382,10 +382,10 @@ void andi_host_pack_pool(const char *const *seqs, const size_t *lens, const size
 						 uint64_t *code, uint64_t *spec, uint64_t *gc, uint64_t *sep);
 }
 
-// The pool from host memory. The characters are packed to 2 bits per base ON THE HOST (host_pack.c:
-// AVX2, all cores) into pinned staging planes and uploaded packed, chunk by chunk, so that packing
-// chunk c + 1 overlaps the upload of chunk c: a quarter of the bytes on PCIe. ANDI_B200_HOST_PACK=0
-// uploads the characters and packs on the device instead (k_pack_tma, what andi_pool_set_device does).
+// The pool from host memory, packed to 2 bits per base ON THE HOST (host_pack.c: AVX2, all cores)
+// into pinned staging planes and uploaded packed, chunk by chunk, so that packing chunk c + 1
+// overlaps the upload of chunk c: a quarter of the bytes on PCIe. Opt-in (ANDI_B200_HOST_PACK=1, see
+// andi_pool_set_host); the default uploads the characters and packs on the device (k_pack_tma).
 static int pool_set_host_packed(andi_ctx *ctx, const char *const *seqs, const size_t *lens, size_t n) {
 	std::vector<size_t> nwords(n);
 	size_t words = 0;
@@ -451,8 +451,12 @@ extern "C" int andi_pool_set_host(andi_ctx *ctx, const char *const *seqs, const 
 	pool_release(ctx);
 	ctx->n = n;
 	ctx->len.assign(lens, lens + n);
+	// Measured on the B200 boxes of this pool (PCIe Gen5: 55 GB/s from pinned memory, 16 host cores):
+	// uploading the characters and packing on the device costs 140 ms for 6.5 GB, packing on the
+	// host first 210 ms -- so the host packer is opt-in (ANDI_B200_HOST_PACK=1: hosts with many
+	// cores behind a slow link).
 	const char *hp = getenv("ANDI_B200_HOST_PACK");
-	if (!(hp && atoi(hp) == 0)) {
+	if (hp && atoi(hp) == 1) {
 		rc = pool_set_host_packed(ctx, seqs, lens, n);
 		if (rc) pool_release(ctx);
 		return rc;
@@ -465,8 +469,15 @@ extern "C" int andi_pool_set_host(andi_ctx *ctx, const char *const *seqs, const 
 	}
 	unsigned char *d_chars = nullptr;
 	CK(dalloc(ctx, &d_chars, total));
-	for (size_t k = 0; k < n; k++)
-		CK(cudaMemcpyAsync(d_chars + offs[k], seqs[k], lens[k], cudaMemcpyHostToDevice, ctx->stream));
+	// sequences that lie in host memory the way they will lie on the device (one buffer, 16-byte
+	// stride rounding: what a caller with a pool buffer has) go up in ONE copy per run
+	for (size_t k = 0; k < n;) {
+		size_t e = k + 1;
+		while (e < n && seqs[e] == seqs[k] + (offs[e] - offs[k])) e++;
+		const size_t bytes = offs[e - 1] - offs[k] + lens[e - 1];
+		CK(cudaMemcpyAsync(d_chars + offs[k], seqs[k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+		k = e;
+	}
 	ctx->st.h2d_bytes += total;
 	rc = pool_finish(ctx, d_chars, offs);
 	dfree(ctx, d_chars);

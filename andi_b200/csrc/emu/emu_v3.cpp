@@ -23,7 +23,7 @@ typedef uint32_t u32;
 #define V3_SERVE_EVERY 8u
 #define V3_COUNT_STATS 1
 
-enum { ST_trips, ST_ext_trips, ST_cand_trips, ST_steps, ST_lucky_hits, ST_lookups, ST_tag0, ST_tag1, ST_wide_gaps, ST_slow_steps, ST_slow_tail, ST_slow_tag3, ST_wide_pairs, ST_slow_long, ST_cols_trips, ST_pushes, ST_drained, ST_drains, ST_drain_rounds,
+enum { ST_trips, ST_ext_trips, ST_cand_trips, ST_steps, ST_lucky_hits, ST_lookups, ST_tag0, ST_tag1, ST_wide_gaps, ST_slow_steps, ST_slow_tail, ST_slow_tag3, ST_wide_pairs, ST_slow_long, ST_cols_trips, ST_pushes, ST_drained, ST_drains, ST_drain_rounds, ST_double_hits,
 	   ST_warp_trips, ST_running_lanes, ST_services, ST_served_lanes, ST_N };
 static u64 *g_stats = nullptr;
 #define V3_STAT(name)                \
@@ -35,6 +35,7 @@ static inline u32 v3_ctz64(u64 x) { return (u32)__builtin_ctzll(x); }
 static inline u32 v3_ctz32(u32 x) { return x ? (u32)__builtin_ctz(x) : 32u; }
 static inline u32 v3_popc32(u32 x) { return (u32)__builtin_popcount(x); }
 static inline u64 v3_ld_fdir(const u64 *p) { return *p; }
+static inline u32 v3_ld_sa(const u32 *p) { return *p; }
 static inline void v3_window64(const u64 *w, u32 pos, u64 &lo, u64 &hi) {
 	u32 i = pos >> 5, sh = (pos & 31u) * 2u;
 	u64 a = w[i], b = w[i + 1], c = w[i + 2];
@@ -195,7 +196,7 @@ extern "C" long emu_walk_v3(const u64 *s_code, u32 N, u32 mid, const u32 *SA, co
 							u32 *records, u64 *stats, u32 n_warps) {
 	if (!s_code || !SA || !fdir || !pool_code || !records || threshold > V3_MAX_T || K > (int)threshold || (int)threshold > K + 15 || n_warps == 0) return -1;
 	V3Const c;
-	c.t = threshold, c.N = N, c.mid = mid, c.border = N / 2, c.chunk = chunk, c.cpq = cpq, c.K = K, c.s_code = s_code, c.fdir = fdir;
+	c.t = threshold, c.N = N, c.mid = mid, c.border = N / 2, c.chunk = chunk, c.cpq = cpq, c.K = K, c.s_code = s_code, c.fdir = fdir, c.SA = SA;
 	Env env;
 	env.h.s_code = s_code, env.h.SA = SA, env.h.N = N, env.h.mid = mid;
 	env.total = (u64)nq * cpq, env.records = records, env.pool_code = pool_code, env.q_off = q_word_off, env.q_len = q_len;

@@ -267,7 +267,7 @@ static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
 		CK(cudaMemsetAsync(b.hist_alloc, 0, 4 * sizeof(u32), ctx->stream));
 		b.hist = b.hist_alloc + 4;
 		CK(dalloc(ctx, &b.bstart, kmers + 1));
-		CK(dalloc(ctx, &b.scan_state, (kmers + 1) / ANDI_SCAN_TILE + 2));
+		CK(dalloc(ctx, &b.scan_state, 1024));  // one word per CTA of k_scan_buckets
 		b.kmers_cap = kmers;
 	}
 	if (N > b.n_cap) {
@@ -283,9 +283,13 @@ static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
 // Exclusive prefix sums of hist[0, n) into out[0, n] (out may be hist), see k_scan_buckets.
 static int scan_buckets(andi_ctx *ctx, const u32 *hist, size_t n, u32 *out, u64 *dir64) {
 	auto &b = ctx->bs;
-	const unsigned tiles = nblocks(n + 1, ANDI_SCAN_TILE);
-	CK(cudaMemsetAsync(b.scan_state, 0, ((size_t)tiles + 1) * sizeof(unsigned long long), ctx->stream));
-	k_scan_buckets<<<tiles, 256, 0, ctx->stream>>>(hist, (u32)n, out, dir64, b.scan_state, reinterpret_cast<u32 *>(b.scan_state + tiles));
+	// co-resident grid: two CTAs of 256 threads per SM (the kernel spins on its predecessors' sums)
+	unsigned ctas = (unsigned)ctx->sm_count * 2u;
+	const size_t tiles = (n + ANDI_SCAN_TILE - 1) / ANDI_SCAN_TILE;
+	if (tiles < ctas) ctas = (unsigned)std::max<size_t>(tiles, 1);
+	const u32 per_cta = (u32)(((tiles + ctas - 1) / ctas) * ANDI_SCAN_TILE);
+	CK(cudaMemsetAsync(b.scan_state, 0, (size_t)ctas * sizeof(unsigned long long), ctx->stream));
+	k_scan_buckets<<<ctas, 256, 0, ctx->stream>>>(hist, (u32)n, per_cta, out, dir64, b.scan_state);
 	ctx->st.esa_launches++;
 	return ANDI_OK;
 }

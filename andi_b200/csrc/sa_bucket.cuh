@@ -380,83 +380,105 @@ __global__ void k_bucket_sort_slots(TextView rs, int K, u32 *__restrict__ SA, u6
 	}
 }
 
-// ---- k_scan_buckets: exclusive prefix sums over the k-mer histogram in ONE pass (decoupled
-// look-back over tiles of ANDI_SCAN_TILE keys; stands where round 1 called cub::DeviceScan).
+// ---- k_scan_buckets: exclusive prefix sums over the k-mer histogram in one launch (stands where
+// round 1 called cub::DeviceScan). The grid is small enough to be co-resident (two CTAs per SM),
+// every CTA owns one contiguous stretch of keys: (1) it sums its stretch and publishes the sum,
+// (2) its threads wait for the sums of all CTAs before it and add them up -- everybody is resident,
+// so nobody waits for a CTA that cannot run --, (3) it scans its stretch tile by tile.
 // out[k] = number of suffixes in buckets < k (may alias hist: the histogram becomes the scatter
 // cursor), out[n] = N. With dir64 given, the directory entries of EMPTY buckets are written on
 // the way (first = end of the bucket, count 0): k_bucket_sort_slots never sees those buckets.
 #define ANDI_SCAN_TILE 4096u  // 256 threads x 16 keys
-__global__ void __launch_bounds__(256) k_scan_buckets(const u32 *hist, u32 n, u32 *out, u64 *__restrict__ dir64,
-													  unsigned long long *tile_state, u32 *tile_ticket) {
-	__shared__ u32 warp_sum[8];
-	__shared__ u32 s_tile, s_prefix;
-	if (threadIdx.x == 0) s_tile = atomicAdd(tile_ticket, 1u);	// tiles start in ticket order: no deadlock
+__device__ __forceinline__ u32 block_sum_256(u32 v, u32 *warp_sum) {
+	for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	__syncthreads();  // warp_sum may still be read from the previous use
+	if ((threadIdx.x & 31u) == 0) warp_sum[threadIdx.x >> 5] = v;
 	__syncthreads();
-	const u32 tile = s_tile, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-	const u32 base = tile * ANDI_SCAN_TILE + threadIdx.x * 16u;
-	u32 v[16];
+	u32 t = 0;
 #pragma unroll
-	for (int q = 0; q < 4; q++) {
-		uint4 x = make_uint4(0, 0, 0, 0);
-		if (base + 4u * q + 3u < n)
-			x = *reinterpret_cast<const uint4 *>(hist + base + 4u * q);
-		else {
-			if (base + 4u * q + 0u < n) x.x = hist[base + 4u * q + 0u];
-			if (base + 4u * q + 1u < n) x.y = hist[base + 4u * q + 1u];
-			if (base + 4u * q + 2u < n) x.z = hist[base + 4u * q + 2u];
-		}
-		v[4 * q] = x.x, v[4 * q + 1] = x.y, v[4 * q + 2] = x.z, v[4 * q + 3] = x.w;
-	}
-	u32 mine = 0;
-#pragma unroll
-	for (int q = 0; q < 16; q++) mine += v[q];
-	u32 inc = mine;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		u32 y = __shfl_up_sync(0xffffffffu, inc, d);
-		if (lane >= (u32)d) inc += y;
-	}
-	if (lane == 31u) warp_sum[wid] = inc;
-	__syncthreads();
-	u32 before = 0, total = 0;
-#pragma unroll
-	for (u32 k = 0; k < 8; k++) {
-		const u32 ws = warp_sum[k];
-		before += k < wid ? ws : 0u;
-		total += ws;
-	}
-	// tile_state[t] = value | status << 62: 1 = the tile's own sum, 2 = sum of all tiles up to and including t
-	if (threadIdx.x == 0) {
-		volatile unsigned long long *st = tile_state;
-		if (tile == 0) {
-			st[0] = (2ULL << 62) | total;
-			s_prefix = 0;
-		} else {
-			st[tile] = (1ULL << 62) | total;
-			u32 prefix = 0;
-			for (u32 t = tile; t-- > 0;) {
-				unsigned long long x;
-				do x = st[t];
-				while ((x >> 62) == 0ULL);
-				prefix += (u32)x;
-				if ((x >> 62) == 2ULL) break;
-			}
-			st[tile] = (2ULL << 62) | (unsigned long long)(prefix + total);
-			s_prefix = prefix;
-		}
-	}
-	__syncthreads();
-	u32 run = s_prefix + before + inc - mine;
-	const u32 end = n;	// out has n + 1 entries
-#pragma unroll
-	for (int q = 0; q < 16; q++) {
-		const u32 k = base + (u32)q;
-		if (k <= end) out[k] = run;	 // v is zero from n on, so out[n] = N
-		if (dir64 && k < end && v[q] == 0u) dir64[k] = (u64)run;
-		run += v[q];
-	}
+	for (int k = 0; k < 8; k++) t += warp_sum[k];
+	return t;
 }
 
+__global__ void __launch_bounds__(256) k_scan_buckets(const u32 *hist, u32 n, u32 per_cta, u32 *out, u64 *__restrict__ dir64,
+													  unsigned long long *cta_sum) {
+	__shared__ u32 warp_sum[8];
+	const u32 b0 = min(n, blockIdx.x * per_cta), b1 = min(n, b0 + per_cta);	 // per_cta is a multiple of the tile
+	const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	// (1) the sum of the stretch
+	u32 mine = 0;
+	for (u32 k = b0 + threadIdx.x * 4u; k < b1; k += 1024u) {
+		if (k + 3u < b1) {
+			const uint4 x = *reinterpret_cast<const uint4 *>(hist + k);
+			mine += x.x + x.y + x.z + x.w;
+		} else {
+			for (u32 j = k; j < b1; j++) mine += hist[j];
+		}
+	}
+	const u32 total = block_sum_256(mine, warp_sum);
+	volatile unsigned long long *sums = cta_sum;
+	if (threadIdx.x == 0) {
+		__threadfence();
+		sums[blockIdx.x] = (1ULL << 32) | total;
+	}
+	// (2) everything in front of this stretch
+	u32 before = 0;
+	for (u32 c = threadIdx.x; c < blockIdx.x; c += 256u) {
+		unsigned long long x;
+		do x = sums[c];
+		while (!(x >> 32));
+		before += (u32)x;
+	}
+	u32 run0 = block_sum_256(before, warp_sum);
+	// (3) scan the stretch, 4096 keys at a time
+	for (u32 t0 = b0; t0 < b1; t0 += ANDI_SCAN_TILE) {
+		const u32 base = t0 + threadIdx.x * 16u;
+		u32 v[16];
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			uint4 x = make_uint4(0, 0, 0, 0);
+			if (base + 4u * q + 3u < b1)
+				x = *reinterpret_cast<const uint4 *>(hist + base + 4u * q);
+			else {
+				if (base + 4u * q + 0u < b1) x.x = hist[base + 4u * q + 0u];
+				if (base + 4u * q + 1u < b1) x.y = hist[base + 4u * q + 1u];
+				if (base + 4u * q + 2u < b1) x.z = hist[base + 4u * q + 2u];
+			}
+			v[4 * q] = x.x, v[4 * q + 1] = x.y, v[4 * q + 2] = x.z, v[4 * q + 3] = x.w;
+		}
+		u32 part = 0;
+#pragma unroll
+		for (int q = 0; q < 16; q++) part += v[q];
+		u32 inc = part;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= (u32)d) inc += y;
+		}
+		__syncthreads();
+		if (lane == 31u) warp_sum[wid] = inc;
+		__syncthreads();
+		u32 in_front = 0, tile_total = 0;
+#pragma unroll
+		for (u32 k = 0; k < 8; k++) {
+			const u32 ws = warp_sum[k];
+			in_front += k < wid ? ws : 0u;
+			tile_total += ws;
+		}
+		u32 run = run0 + in_front + inc - part;
+#pragma unroll
+		for (int q = 0; q < 16; q++) {
+			const u32 k = base + (u32)q;
+			if (k < b1) {
+				out[k] = run;
+				if (dir64 && v[q] == 0u) dir64[k] = (u64)run;
+			}
+			run += v[q];
+		}
+		run0 += tile_total;
+	}
+	if (blockIdx.x == gridDim.x - 1u && threadIdx.x == 0) out[n] = run0;	// = N (the last CTA ends at n)
+}
 
 // ---- two-level counting sort for DEEP directories (K >= 13: texts of hundreds of Mbp, config 5).
 // A histogram of 4^K counters (1 GB at K = 14) is far beyond L2, and random atomics on it run at

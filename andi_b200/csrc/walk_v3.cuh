@@ -32,6 +32,7 @@ V3_FN u32 v3_ctz64(u64 x) { return (u32)(__ffsll((long long)x) - 1); }
 V3_FN u32 v3_ctz32(u32 x) { return (u32)__clz((int)__brev(x)); }  // 32 for x == 0
 V3_FN u32 v3_popc32(u32 x) { return (u32)__popc(x); }
 V3_FN u64 v3_ld_fdir(const u64 *p) { return __ldg(p); }
+V3_FN u32 v3_ld_sa(const u32 *p) { return __ldg(p); }
 V3_FN void v3_window64(const u64 *__restrict__ w, u32 pos, u64 &lo, u64 &hi) { window64(w, pos, lo, hi); }
 V3_FN u32 v3_kmer_key(u64 win, int k) { return kmer_key(win, k); }
 
@@ -92,7 +93,7 @@ k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32
 	const V3Pend P = {&pend_q[0][threadIdx.x], &pend_s[0][threadIdx.x], &pend_g[0][threadIdx.x]};
 	V3Const c;
 	c.t = threshold, c.N = S.rs.len, c.mid = S.rs.mid, c.border = S.rs.len / 2, c.chunk = chunk, c.cpq = cpq, c.K = S.K;
-	c.s_code = S.rs.code, c.fdir = S.fdir;
+	c.s_code = S.rs.code, c.fdir = S.fdir, c.SA = S.SA;
 	V3Env env = {S, (u64)nq * cpq, records, next_unit, queries, query_ids, threshold};
 	V3Lane L;
 	L.svc = V3_SVC_FETCH, L.job = V3_STEP;

@@ -35,10 +35,14 @@
 #error "define V3_FN and the v3_* primitives before including walk_v3_lane.h"
 #endif
 
-enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V3_SVC_DONE = 4 };
-enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND1 = 3, V3_CAND2 = 4 };
+enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V3_SVC_DONE = 4, V3_SVC_SCAN = 5 };
+enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND1 = 3, V3_CAND2 = 4, V3_RESOLVED = 5 };
+#define V3_SCAN_MAX 8u  // buckets up to this size are scanned by the lean service routine
 
 #define V3_EVEN 0x5555555555555555ULL
+#ifndef V3_DOUBLE_HIT
+#define V3_DOUBLE_HIT 1
+#endif
 #define V3_MAX_T 31u	   // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
 #ifndef V3_PEND_SLOTS
 #define V3_PEND_SLOTS 6u   // pending-gap queue entries per lane (16 columns each)
@@ -49,6 +53,7 @@ struct V3Const {
 	int K;
 	const u64 *s_code;
 	const u64 *fdir;
+	const u32 *SA;
 };
 
 // Chain A is the one being advanced. PHASE 2 carries a second chain B and `a_true` (A is the
@@ -181,7 +186,8 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	v3_window64(L.q_code, wq, q0, q1);
 	v3_window64(c.s_code, ws, s0, s1);
 	const u64 x0 = ((q0 ^ s0) >> (2u * gg)) << (2u * gg);  // gg <= V3_MAX_T
-	const u32 D = v3_first_diff(x0, q1 ^ s1);
+	const u64 x1w = q1 ^ s1;
+	const u32 D = v3_first_diff(x0, x1w);
 	const u32 raw = D - gg;
 	const bool complete = D < 64u || raw >= clim;
 	u32 matched = raw < clim ? raw : clim;
@@ -190,7 +196,7 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	// ---- what the window decides. Deliberately written as selects, not as if-blocks: every branch
 	// region runs with the few lanes that need it while the rest of the warp waits (the first form
 	// of this kernel spent two thirds of its issue slots that way).
-	const bool c1 = job == V3_CAND1, c2 = job == V3_CAND2;
+	const bool c1 = job == V3_CAND1, c2 = job == V3_CAND2, c3 = job == V3_RESOLVED;
 	const u32 l1 = L.len1;
 	// EXT: the anchor grows; done when the window saw its end
 	L.ll += is_ext ? matched : 0u;
@@ -198,13 +204,15 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	// CAND1 (first of two suffixes that carry the k-mer): remember its length, compare the other one.
 	// CAND2: the longer of the two is the match; equal lengths = not unique (process.c:122).
 	// A candidate longer than the window is fine when it is the only / the longer one (EXT follows).
+	// RESOLVED: the service routine has scanned a bucket of three or more (v3_service): best
+	// candidate in cand_p, its length in len1, cand2 = unique; this trip only accounts for it.
 	const bool slow_long = (c1 && !complete) || (c2 && !complete && l1 >= matched);
-	const bool tie = c2 && l1 == matched, first_better = c2 && l1 > matched;
+	const bool tie = (c2 && l1 == matched) || (c3 && L.cand2 == 0u), first_better = c2 && l1 > matched;
 	u32 cur_s = is_cand ? (first_better ? L.cand2 : L.cand_p) : guess;
 	bool in_window = (diag_ok || diag) && !first_better;
-	bool complete_a = complete;	 // the anchor (if any) ends inside what has been compared
-	matched = first_better ? l1 : matched;
-	const bool cand_final = c2 && !slow_long;
+	bool complete_a = complete || c3;  // the anchor (if any) ends inside what has been compared
+	matched = (first_better || c3) ? l1 : matched;
+	const bool cand_final = (c2 && !slow_long) || c3;
 	bool anchor = is_step ? (lucky && matched >= t) : (cand_final && !tie && matched >= t);
 	bool plain_end = cand_final && !anchor;	 // process.c:122: no anchor, pos_Q += length + 1
 	const bool lookup = is_step && !anchor;
@@ -240,33 +248,37 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 			const u64 fe = v3_ld_fdir(c.fdir + v3_kmer_key(kw, c.K));
 			const u32 tag = (u32)(fe >> 62);
 			V3_STAT(lookups);
-			// tag 0, absent k-mer: only the length matters (it is < K <= threshold)
-			plain_end = tag == 0u, matched = (u32)fe;
-			if (tag == 0u) V3_STAT(tag0);
+			// tag 0, absent k-mer: only the length matters (it is < K <= threshold).
 			// tag 1, ONE suffix carries the k-mer: the entry holds its text position and the 15 bases
 			// that follow the k-mer there, so the match length up to K + 15 (>= threshold) comes out
 			// of the entry -- no candidate window, no second trip. A match that long is an anchor at
 			// once (a single candidate is always unique, process.c:122) and grows in EXT trips.
+			// (computed for every lane that looks up, selected by tag: no branch region of its own)
+			const bool t0 = tag == 0u, t1 = tag == 1u;
 			const u32 p1 = (u32)fe & 0x7fffffffu;
-			if (tag == 1u) {
-				V3_STAT(tag1);
-				const u32 x = ((u32)(kw >> (2 * c.K)) ^ (u32)(fe >> 31)) & 0x3fffffffu;
-				const u32 d = v3_ctz32(x) >> 1;	 // 16 when all 15 agree
-				const u32 prun = p1 < c.mid ? c.mid - p1 : (p1 == c.mid ? 0u : c.N - p1), prem = L.qlen - L.pos;
-				const u32 plim = prem < prun ? prem : prun, have = (u32)c.K + (d < 15u ? d : 15u);
-				matched = have < plim ? have : plim;
-				complete_a = d < 15u || have >= plim;
-				anchor = matched >= t, plain_end = !anchor;
-				cur_s = p1, in_window = diag_ok && p1 == guess;
-			}
+			const u32 x = ((u32)(kw >> (2 * c.K)) ^ (u32)(fe >> 31)) & 0x3fffffffu;
+			const u32 d = v3_ctz32(x) >> 1;	 // 16 when all 15 agree
+			const u32 prun = p1 < c.mid ? c.mid - p1 : (p1 == c.mid ? 0u : c.N - p1), prem = L.qlen - L.pos;
+			const u32 plim = prem < prun ? prem : prun, have = (u32)c.K + (d < 15u ? d : 15u);
+			const u32 len1 = have < plim ? have : plim;
+			matched = t0 ? (u32)fe : (t1 ? len1 : matched);
+			complete_a = t1 ? (d < 15u || have >= plim) : complete_a;
+			anchor = t1 && len1 >= t;
+			plain_end = t0 || (t1 && !anchor);
+			cur_s = t1 ? p1 : cur_s;
+			in_window = t1 ? (diag_ok && p1 == guess) : in_window;
+#ifdef V3_COUNT_STATS
+			if (t0) V3_STAT(tag0);
+			if (t1) V3_STAT(tag1);
+#endif
 			// tag 2: two suffixes, both text positions in the entry -- the one that could pair goes
 			// last so that its window is the one at hand when the anchor is accounted
 			const u32 p2 = (u32)(fe >> 31) & 0x7fffffffu;
 			const bool p1_diag = p1 - end_s == g;
 			if (tag == 2u) L.cand_p = p1_diag ? p2 : p1, L.cand2 = p1_diag ? p1 : p2, L.job = V3_CAND1;
-			if (tag == 3u) {
+			if (tag == 3u) {  // three or more: the service routine scans the bucket
 				V3_STAT(slow_tag3);
-				L.svc = V3_SVC_SLOW;
+				L.cand_p = (u32)fe, L.cand2 = (u32)(fe >> 32) & 0x3fffffffu, L.svc = V3_SVC_SCAN;
 			}
 		}
 	}
@@ -302,6 +314,37 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 		}
 	}
 	if (push_n) v3_push_gap(L, P, q0, s0, push_n, sign);
+#if V3_DOUBLE_HIT
+	// A SECOND lucky anchor out of the same window: the step that follows a lucky anchor starts one
+	// column behind the mismatch that ended it (gap = that one column) on the same diagonal, so its
+	// compare is already in the XOR of this window. If the next run of matches is an anchor too
+	// (process.c:82-100 again), it is accounted here and the lane saves a whole trip. PHASE 1 only:
+	// the boundary replay looks at both chains before every step.
+	if (PHASE == 1 && anchor && is_step && lucky && !lookup && complete && D < 63u && L.pos < L.c_end) {
+		const u32 c0 = D + 1u;	// window column of the new pos_Q
+		const u64 y0 = c0 < 32u ? (x0 >> (2u * c0)) << (2u * c0) : 0ULL;
+		const u64 y1 = c0 < 32u ? x1w : (x1w >> (2u * (c0 - 32u))) << (2u * (c0 - 32u));
+		const u32 D2 = v3_first_diff(y0, y1), raw2 = D2 - c0, clim2 = clim - (matched + 1u);
+		const bool complete2 = D2 < 64u || raw2 >= clim2;
+		const u32 matched2 = raw2 < clim2 ? raw2 : clim2;
+		if (matched2 >= t) {
+			V3_STAT(steps);
+			V3_STAT(lucky_hits);
+			V3_STAT(double_hits);
+			const u32 s2 = L.ls + L.ll + 1u;  // process.c:91
+			const bool pairs2 = (s2 < c.border) == (L.ls < c.border);
+			if (pairs2 || L.paired || L.ll >= 2u * t) L.sumq += L.ll >> 2, L.sumr += L.ll & 3u;
+			if (pairs2) {
+				const u64 sw = D < 32u ? s0 : s1, qw = D < 32u ? q0 : q1;
+				const u32 sh = 2u * (D & 31u);
+				col[((((u32)(sw >> sh) & 3u) << 2) | ((u32)(qw >> sh) & 3u)) * V3_CELL_STRIDE] += 1u;
+			}
+			L.ls = s2, L.lq = L.pos, L.ll = matched2, L.paired = pairs2 ? 1u : 0u;
+			if (complete2) L.pos += matched2 + 1u;
+			L.job = complete2 ? V3_STEP : V3_EXT;
+		}
+	}
+#endif
 }
 
 // Classify everything this lane has queued.
@@ -376,6 +419,34 @@ V3_FN void v3_finish_unit(const V3Lane &L, u32 *rec, const u32 *col) {
 //   v3_begin_unit; false = no work in this unit); void slow_step(V3Lane &, u32 *col, u32 sign).
 template <int PHASE, class Env>
 V3_FN void v3_service(V3Lane &L, const V3Const &c, Env &env, u32 *col, const V3Pend &P) {
+	if (L.svc == V3_SVC_SCAN) {
+		// a bucket of three or more suffixes (L.cand_p = first SA index, L.cand2 = their number):
+		// compare each with the query through one 64-column window; the longest is the match,
+		// unique if no other is as long (process.c:117-122). Repeats longer than a window and big
+		// buckets are left to the generic step.
+		const u32 first = L.cand_p, count = L.cand2, rem = L.qlen - L.pos;
+		u32 best = 0, best_p = 0, best_n = 0;
+		bool ok = count <= V3_SCAN_MAX;
+		u64 q0, q1;
+		v3_window64(L.q_code, L.pos, q0, q1);
+		for (u32 k = 0; ok && k < count; k++) {
+			const u32 p = v3_ld_sa(c.SA + first + k);
+			u64 s0, s1;
+			v3_window64(c.s_code, p, s0, s1);
+			const u32 D = v3_first_diff(q0 ^ s0, q1 ^ s1);
+			const u32 run = p < c.mid ? c.mid - p : (p == c.mid ? 0u : c.N - p), lim = rem < run ? rem : run;
+			ok = D < 64u || D >= lim;
+			const u32 m = D < lim ? D : lim;
+			best_n = m > best ? 1u : (m == best ? best_n + 1u : best_n);
+			best_p = m > best ? p : best_p;
+			best = m > best ? m : best;
+		}
+		if (ok) {
+			L.cand_p = best_p, L.len1 = best, L.cand2 = best_n == 1u ? 1u : 0u, L.job = V3_RESOLVED, L.svc = V3_RUN;
+			return;
+		}
+		L.svc = V3_SVC_SLOW;
+	}
 	if (L.svc == V3_SVC_SLOW) {
 		env.slow_step(L, col, (PHASE == 2 && !L.a_true) ? 0xffffffffu : 1u);
 		L.svc = V3_RUN;

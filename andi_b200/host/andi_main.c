@@ -236,14 +236,32 @@ int main(int argc, char *argv[]) {
 			usage(EXIT_FAILURE);
 	}
 
+	/* every file is read by one thread (src/io.c:159-233 reads them one after the other); sequences,
+	 * flags and warnings are then collected in file order, so nothing depends on the thread count */
 	host_seqs seqs;
 	seqs_init(&seqs);
-	for (size_t i = 0; i < files.size; i++) {
-		if (cfg.flags & HF_JOIN)
-			fasta_read_join(files.data[i], &seqs, &cfg.flags);
-		else
-			fasta_read(files.data[i], &seqs, &cfg.flags);
-		free(files.data[i]);
+	{
+		host_seqs *part = calloc(files.size ? files.size : 1, sizeof *part);
+		int *part_flags = calloc(files.size ? files.size : 1, sizeof *part_flags);
+		char(*msg)[512] = calloc(files.size ? files.size : 1, sizeof *msg);
+		if (!part || !part_flags || !msg) err(errno, "Out of memory");
+		const int join = (cfg.flags & HF_JOIN) != 0;
+#pragma omp parallel for schedule(dynamic, 1)
+		for (size_t i = 0; i < files.size; i++) {
+			seqs_init(&part[i]);
+			if (join)
+				fasta_read_join_quiet(files.data[i], &part[i], &part_flags[i], msg[i], sizeof msg[i]);
+			else
+				fasta_read_quiet(files.data[i], &part[i], &part_flags[i], msg[i], sizeof msg[i]);
+		}
+		for (size_t i = 0; i < files.size; i++) {
+			if (msg[i][0]) warnx("%s", msg[i]);
+			cfg.flags |= part_flags[i];
+			for (size_t k = 0; k < part[i].size; k++) seqs_push(&seqs, part[i].data[k]);
+			free(part[i].data); /* the sequences themselves moved into seqs */
+			free(files.data[i]);
+		}
+		free(part), free(part_flags), free(msg);
 	}
 	free(files.data);
 

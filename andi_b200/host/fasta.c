@@ -9,6 +9,7 @@
 #include <ctype.h>
 #include <err.h>
 #include <errno.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -82,12 +83,15 @@ static size_t normalize_into(char *dst, const char *src, size_t n, int *non_acgt
 	return w;
 }
 
-int fasta_read(const char *file_name, host_seqs *out, int *flags) {
+/* The reader proper. It prints nothing: a failure leaves its message in msg (what the reference
+ * would have warned), so that files can be read by several threads and reported in order. */
+int fasta_read_quiet(const char *file_name, host_seqs *out, int *flags, char *msg, size_t msg_len) {
 	size_t len = 0;
+	if (msg_len) msg[0] = '\0';
 	char *buf = slurp(file_name, &len);
 	if (!buf) {
 		*flags |= HF_SOFT_ERROR;
-		warn("%s", file_name);
+		snprintf(msg, msg_len, "%s: %s", file_name, strerror(errno));
 		return 1;
 	}
 	const char *fail = NULL;
@@ -154,16 +158,30 @@ int fasta_read(const char *file_name, host_seqs *out, int *flags) {
 	free(buf);
 	if (fail) {
 		*flags |= HF_SOFT_ERROR;
-		warnx("%s: %s", file_name, fail);
+		snprintf(msg, msg_len, "%s: %s", file_name, fail);
 		return 1;
 	}
 	return 0;
 }
 
+int fasta_read(const char *file_name, host_seqs *out, int *flags) {
+	char msg[512];
+	int rc = fasta_read_quiet(file_name, out, flags, msg, sizeof msg);
+	if (msg[0]) warnx("%s", msg);
+	return rc;
+}
+
 int fasta_read_join(const char *file_name, host_seqs *out, int *flags) {
+	char msg[512];
+	int rc = fasta_read_join_quiet(file_name, out, flags, msg, sizeof msg);
+	if (msg[0]) warnx("%s", msg);
+	return rc;
+}
+
+int fasta_read_join_quiet(const char *file_name, host_seqs *out, int *flags, char *msg, size_t msg_len) {
 	host_seqs single;
 	seqs_init(&single);
-	fasta_read(file_name, &single, flags);
+	fasta_read_quiet(file_name, &single, flags, msg, msg_len);
 	if (single.size == 0) {
 		seqs_free(&single);
 		return 1;

@@ -1,16 +1,11 @@
 #!/bin/bash
 # scratch job for the GPU box (edited per run)
-python tools/debug_build.py 2>&1 | grep -v " ok" | tail -5
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_shapes.py tests/test_gpu_compat.py -m gpu -x -q 2>&1 | tail -5
-ANDI_B200_DEPTH_BIAS=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2g_launches_c4.csv python tools/launch_list.py 64 2100000 3 > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2g_launches_c5.csv python tools/launch_list.py 2 120000000 1 > /dev/null 2>&1
-python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu --no-e2e --no-full --rows 4 | cut -c1-150
-python - <<'PY'
-import torch, time
-x = torch.empty(6_000_000_000, dtype=torch.uint8, pin_memory=True)
-y = torch.empty_like(x, device="cuda")
-for _ in range(2):
-    torch.cuda.synchronize(); t = time.perf_counter(); y.copy_(x, non_blocking=True); torch.cuda.synchronize()
-    print("H2D pinned 6 GB: %.1f GB/s" % (6.0 / (time.perf_counter() - t)))
+python tools/debug_build.py 2>&1 | grep -v " ok" | tail -3
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_shapes.py tests/test_gpu_compat.py tests/test_gpu_cli.py tests/test_gpu_relink.py -m gpu -x -q -k "not c5 and not very_large" 2>&1 | tail -5
+tools/bench_variants.sh b
+ANDI_B200_DEPTH_BIAS=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2h_launches_c4.csv python tools/launch_list.py 64 2100000 3 > /dev/null 2>&1
+python bench.py --steps 3 --warmup 3 --no-cpu --no-full > gpurun_out/r2h_bench.json 2> gpurun_out/r2h_bench.err; python - <<'PY'
+import json
+d=json.load(open("gpurun_out/r2h_bench.json")); print("c4", d["value"], d["ms_per_step"], d["e2e"], d["esa_build"]["ms_per_subject"], d["roofline"]["launch_ms"], d["cub_calls"])
 PY
-lscpu | grep -E "Model name|^CPU\(s\)|Flags" | cut -c1-400
+for w in c2 c3; do python bench.py --workload $w --steps 3 --warmup 3 --no-cpu --no-e2e --no-full --rows 29 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$w', d['value'], d['ms_per_step'], d['esa_build']['ms_per_subject'], d['roofline']['launch_ms'], d['cub_calls'])"; done
