@@ -430,25 +430,20 @@ __global__ void __launch_bounds__(256) k_scan_buckets(const u32 *hist, u32 n, u3
 		before += (u32)x;
 	}
 	u32 run0 = block_sum_256(before, warp_sum);
-	// (3) scan the stretch, 4096 keys at a time
-	for (u32 t0 = b0; t0 < b1; t0 += ANDI_SCAN_TILE) {
-		const u32 base = t0 + threadIdx.x * 16u;
-		u32 v[16];
-#pragma unroll
-		for (int q = 0; q < 4; q++) {
-			uint4 x = make_uint4(0, 0, 0, 0);
-			if (base + 4u * q + 3u < b1)
-				x = *reinterpret_cast<const uint4 *>(hist + base + 4u * q);
-			else {
-				if (base + 4u * q + 0u < b1) x.x = hist[base + 4u * q + 0u];
-				if (base + 4u * q + 1u < b1) x.y = hist[base + 4u * q + 1u];
-				if (base + 4u * q + 2u < b1) x.z = hist[base + 4u * q + 2u];
-			}
-			v[4 * q] = x.x, v[4 * q + 1] = x.y, v[4 * q + 2] = x.z, v[4 * q + 3] = x.w;
+	// (3) scan the stretch, 1024 keys at a time: thread t owns keys 4t .. 4t+3 of the tile, so that
+	// loads and stores are 16 contiguous bytes per lane (a thread that owns 16 consecutive keys makes
+	// every load and store touch 32 different sectors: measured 245 us instead of 35 for 4^12 keys)
+	for (u32 t0 = b0; t0 < b1; t0 += 1024u) {
+		const u32 base = t0 + threadIdx.x * 4u;
+		uint4 x = make_uint4(0, 0, 0, 0);
+		if (base + 3u < b1)
+			x = *reinterpret_cast<const uint4 *>(hist + base);
+		else {
+			if (base + 0u < b1) x.x = hist[base + 0u];
+			if (base + 1u < b1) x.y = hist[base + 1u];
+			if (base + 2u < b1) x.z = hist[base + 2u];
 		}
-		u32 part = 0;
-#pragma unroll
-		for (int q = 0; q < 16; q++) part += v[q];
+		const u32 part = x.x + x.y + x.z + x.w;
 		u32 inc = part;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
@@ -465,15 +460,19 @@ __global__ void __launch_bounds__(256) k_scan_buckets(const u32 *hist, u32 n, u3
 			in_front += k < wid ? ws : 0u;
 			tile_total += ws;
 		}
-		u32 run = run0 + in_front + inc - part;
-#pragma unroll
-		for (int q = 0; q < 16; q++) {
-			const u32 k = base + (u32)q;
-			if (k < b1) {
-				out[k] = run;
-				if (dir64 && v[q] == 0u) dir64[k] = (u64)run;
-			}
-			run += v[q];
+		const u32 r0 = run0 + in_front + inc - part, r1 = r0 + x.x, r2 = r1 + x.y, r3 = r2 + x.z;
+		if (base + 3u < b1) {
+			*reinterpret_cast<uint4 *>(out + base) = make_uint4(r0, r1, r2, r3);
+		} else {
+			if (base + 0u < b1) out[base + 0u] = r0;
+			if (base + 1u < b1) out[base + 1u] = r1;
+			if (base + 2u < b1) out[base + 2u] = r2;
+		}
+		if (dir64) {
+			if (base + 0u < b1 && x.x == 0u) dir64[base + 0u] = (u64)r0;
+			if (base + 1u < b1 && x.y == 0u) dir64[base + 1u] = (u64)r1;
+			if (base + 2u < b1 && x.z == 0u) dir64[base + 2u] = (u64)r2;
+			if (base + 3u < b1 && x.w == 0u) dir64[base + 3u] = (u64)r3;
 		}
 		run0 += tile_total;
 	}

@@ -40,9 +40,6 @@ enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND1 = 3, V3_CAND2 = 4, V
 #define V3_SCAN_MAX 8u  // buckets up to this size are scanned by the lean service routine
 
 #define V3_EVEN 0x5555555555555555ULL
-#ifndef V3_DOUBLE_HIT
-#define V3_DOUBLE_HIT 1
-#endif
 #define V3_MAX_T 31u	   // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
 #ifndef V3_PEND_SLOTS
 #define V3_PEND_SLOTS 6u   // pending-gap queue entries per lane (16 columns each)
@@ -186,8 +183,7 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	v3_window64(L.q_code, wq, q0, q1);
 	v3_window64(c.s_code, ws, s0, s1);
 	const u64 x0 = ((q0 ^ s0) >> (2u * gg)) << (2u * gg);  // gg <= V3_MAX_T
-	const u64 x1w = q1 ^ s1;
-	const u32 D = v3_first_diff(x0, x1w);
+	const u32 D = v3_first_diff(x0, q1 ^ s1);
 	const u32 raw = D - gg;
 	const bool complete = D < 64u || raw >= clim;
 	u32 matched = raw < clim ? raw : clim;
@@ -314,37 +310,6 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 		}
 	}
 	if (push_n) v3_push_gap(L, P, q0, s0, push_n, sign);
-#if V3_DOUBLE_HIT
-	// A SECOND lucky anchor out of the same window: the step that follows a lucky anchor starts one
-	// column behind the mismatch that ended it (gap = that one column) on the same diagonal, so its
-	// compare is already in the XOR of this window. If the next run of matches is an anchor too
-	// (process.c:82-100 again), it is accounted here and the lane saves a whole trip. PHASE 1 only:
-	// the boundary replay looks at both chains before every step.
-	if (PHASE == 1 && anchor && is_step && lucky && !lookup && complete && D < 63u && L.pos < L.c_end) {
-		const u32 c0 = D + 1u;	// window column of the new pos_Q
-		const u64 y0 = c0 < 32u ? (x0 >> (2u * c0)) << (2u * c0) : 0ULL;
-		const u64 y1 = c0 < 32u ? x1w : (x1w >> (2u * (c0 - 32u))) << (2u * (c0 - 32u));
-		const u32 D2 = v3_first_diff(y0, y1), raw2 = D2 - c0, clim2 = clim - (matched + 1u);
-		const bool complete2 = D2 < 64u || raw2 >= clim2;
-		const u32 matched2 = raw2 < clim2 ? raw2 : clim2;
-		if (matched2 >= t) {
-			V3_STAT(steps);
-			V3_STAT(lucky_hits);
-			V3_STAT(double_hits);
-			const u32 s2 = L.ls + L.ll + 1u;  // process.c:91
-			const bool pairs2 = (s2 < c.border) == (L.ls < c.border);
-			if (pairs2 || L.paired || L.ll >= 2u * t) L.sumq += L.ll >> 2, L.sumr += L.ll & 3u;
-			if (pairs2) {
-				const u64 sw = D < 32u ? s0 : s1, qw = D < 32u ? q0 : q1;
-				const u32 sh = 2u * (D & 31u);
-				col[((((u32)(sw >> sh) & 3u) << 2) | ((u32)(qw >> sh) & 3u)) * V3_CELL_STRIDE] += 1u;
-			}
-			L.ls = s2, L.lq = L.pos, L.ll = matched2, L.paired = pairs2 ? 1u : 0u;
-			if (complete2) L.pos += matched2 + 1u;
-			L.job = complete2 ? V3_STEP : V3_EXT;
-		}
-	}
-#endif
 }
 
 // Classify everything this lane has queued.

@@ -20,7 +20,7 @@ UNIT_WORDS = 38
 CODE = np.full(256, 255, dtype=np.uint8)
 for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3), (b"#", 1)):
     CODE[ch[0]] = v
-STATS = ["trips", "ext_trips", "cand_trips", "steps", "lucky_hits", "lookups", "tag0", "tag1", "wide_gaps", "slow_steps", "slow_tail", "slow_tag3", "wide_pairs", "slow_long", "cols_trips", "pushes", "drained", "drains", "drain_rounds", "double_hits",
+STATS = ["trips", "ext_trips", "cand_trips", "steps", "lucky_hits", "lookups", "tag0", "tag1", "wide_gaps", "slow_steps", "slow_tail", "slow_tag3", "wide_pairs", "slow_long", "cols_trips", "pushes", "drained", "drains", "drain_rounds",
          "warp_trips", "running_lanes", "services", "served_lanes"]
 
 

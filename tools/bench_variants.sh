@@ -12,6 +12,6 @@ for lib in andi_b200/libandi_b200.so andi_b200/variants/libandi_b200_*.so; do
 import json, sys
 d = json.loads(sys.argv[2])
 n = d["config"]["rows_per_step_per_gpu"] * d["steps"]
-print(f"{sys.argv[1]:32s} {d['value']:10.0f} pairs/s  walk {d['walk_ms_total'] / n:6.3f} ms/subject  esa {d['esa_ms_total'] / n:6.3f}")
+print(f"{sys.argv[1]:32s} {d['value']:10.0f} pairs/s  walk {d["kernel_ms_sums_of_timed_steps"]["walk"] / n:6.3f} ms/subject  esa {d["kernel_ms_sums_of_timed_steps"]["esa"] / n:6.3f}")
 PY
 done
