@@ -38,6 +38,12 @@ struct andi_ctx {
 	std::vector<size_t> word_off;  // u64-word offset of each sequence's planes
 	u64 *pool_code = nullptr, *pool_spec = nullptr;
 	size_t pool_words = 0;
+	// The planes and the character staging buffer are KEPT across pools (capacities below): setting a
+	// pool of the same size again allocates nothing. (Re-allocating 10 GB per call made every second
+	// andi_pool_set_host take 0.7 - 2.5 s instead of 0.12 s while the memory pool re-mapped.)
+	size_t plane_cap = 0;
+	unsigned char *stage_chars = nullptr;
+	size_t stage_cap = 0;
 	uint4 *pool_comp = nullptr;	 // prefix composition per word, built on first LOGDET / ANI use
 	unsigned char *pool_sep3 = nullptr;	 // separator hints per word, built on first join-mode walk
 	QueryView *d_queries = nullptr;
@@ -212,10 +218,10 @@ static void pool_release(andi_ctx *ctx) {
 	if (ctx->helper) ctx->helper->n = 0;  // its borrowed pointers die with this pool
 	if (ctx->borrowed_pool) {
 		ctx->pool_code = ctx->pool_spec = nullptr, ctx->pool_comp = nullptr, ctx->pool_sep3 = nullptr, ctx->d_queries = nullptr;
+		ctx->plane_cap = 0;
 		ctx->borrowed_pool = false;
 	}
-	dfree(ctx, ctx->pool_code);
-	dfree(ctx, ctx->pool_spec);
+	// (pool_code / pool_spec stay allocated for the next pool: planes_ensure)
 	dfree(ctx, ctx->pool_comp);
 	dfree(ctx, ctx->pool_sep3);
 	dfree(ctx, ctx->d_queries);
@@ -238,6 +244,7 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	harvest_events(ctx);
 	pool_release(ctx);
+	dfree(ctx, ctx->pool_code), dfree(ctx, ctx->pool_spec), dfree(ctx, ctx->stage_chars);
 	dfree(ctx, ctx->bs.hist_alloc), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
 	dfree(ctx, ctx->bs.scan_state);
 	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter);
@@ -297,6 +304,19 @@ extern "C" size_t andi_threshold(double p_value, double gc, size_t rs_len) {
 
 // ------------------------------------------------------------------ pool
 
+// Planes for a pool of `words` words: the ones this context already has, if they are large enough.
+static int planes_ensure(andi_ctx *ctx, size_t words) {
+	if (words > ctx->plane_cap) {
+		dfree(ctx, ctx->pool_code), dfree(ctx, ctx->pool_spec);
+		ctx->plane_cap = 0;
+		CK(dalloc(ctx, &ctx->pool_code, words));
+		CK(dalloc(ctx, &ctx->pool_spec, words));
+		ctx->plane_cap = words;
+	}
+	ctx->pool_words = words;
+	return ANDI_OK;
+}
+
 static int pool_finish(andi_ctx *ctx, const unsigned char *d_chars, const std::vector<size_t> &offs) {
 	// d_chars: all sequences in HBM; pack them, count GC and separators.
 	const size_t n = ctx->n;
@@ -306,9 +326,10 @@ static int pool_finish(andi_ctx *ctx, const unsigned char *d_chars, const std::v
 		ctx->word_off[k] = words;
 		words += (plane_words(ctx->len[k]) + 1) & ~(size_t)1;  // keep 16-byte alignment
 	}
-	CK(dalloc(ctx, &ctx->pool_code, words));
-	CK(dalloc(ctx, &ctx->pool_spec, words));
-	ctx->pool_words = words;
+	{
+		int rc = planes_ensure(ctx, words);
+		if (rc) return rc;
+	}
 	unsigned long long *d_cnt = nullptr;
 	CK(dalloc(ctx, &d_cnt, 2 * n));
 	CK(cudaMemsetAsync(d_cnt, 0, 2 * n * sizeof(unsigned long long), ctx->stream));
@@ -403,9 +424,10 @@ static int pool_set_host_packed(andi_ctx *ctx, const char *const *seqs, const si
 		CK(cudaHostAlloc((void **)&ctx->h_spec, words * sizeof(u64), cudaHostAllocDefault));
 		ctx->h_words = words;
 	}
-	CK(dalloc(ctx, &ctx->pool_code, words));
-	CK(dalloc(ctx, &ctx->pool_spec, words));
-	ctx->pool_words = words;
+	{
+		int rc = planes_ensure(ctx, words);
+		if (rc) return rc;
+	}
 	std::vector<uint64_t> gc(n), sep(n);
 	const size_t chunk_chars = (size_t)256 << 20;
 	for (size_t k0 = 0; k0 < n;) {
@@ -467,20 +489,25 @@ extern "C" int andi_pool_set_host(andi_ctx *ctx, const char *const *seqs, const 
 		offs[k] = total;
 		total += (lens[k] + 15) & ~(size_t)15;
 	}
-	unsigned char *d_chars = nullptr;
-	CK(dalloc(ctx, &d_chars, total));
+	if (total > ctx->stage_cap) {
+		dfree(ctx, ctx->stage_chars);
+		ctx->stage_cap = 0;
+		CK(dalloc(ctx, &ctx->stage_chars, total));
+		ctx->stage_cap = total;
+	}
+	unsigned char *d_chars = ctx->stage_chars;
 	// sequences that lie in host memory the way they will lie on the device (one buffer, 16-byte
 	// stride rounding: what a caller with a pool buffer has) go up in ONE copy per run
+	const bool split = getenv("ANDI_B200_SPLIT_UPLOAD") != nullptr;	 // experiments: one copy per sequence
 	for (size_t k = 0; k < n;) {
 		size_t e = k + 1;
-		while (e < n && seqs[e] == seqs[k] + (offs[e] - offs[k])) e++;
+		while (e < n && !split && seqs[e] == seqs[k] + (offs[e] - offs[k]) && offs[e] - offs[k] < ((size_t)512 << 20)) e++;
 		const size_t bytes = offs[e - 1] - offs[k] + lens[e - 1];
 		CK(cudaMemcpyAsync(d_chars + offs[k], seqs[k], bytes, cudaMemcpyHostToDevice, ctx->stream));
 		k = e;
 	}
 	ctx->st.h2d_bytes += total;
 	rc = pool_finish(ctx, d_chars, offs);
-	dfree(ctx, d_chars);
 	if (rc) pool_release(ctx);
 	return rc;
 }

@@ -243,6 +243,28 @@ struct PresenceLevels {
 	u32 offset[16];	 // word offset of level m
 };
 
+// All levels below `top` from level `top` in ONE launch of a single CTA (each level is a quarter of
+// the one above: from level K-2 down they are small enough for one CTA, and ten launches of a
+// microsecond each cost more than the work).
+__global__ void __launch_bounds__(1024) k_presence_down_all(PresenceLevels lv, int top) {
+	for (int m = top - 1; m >= 1; m--) {
+		const u32 nbits = 1u << (2 * m);
+		const u32 *upper = lv.bits + lv.offset[m + 1];
+		u32 *lower = lv.bits + lv.offset[m];
+		for (u32 w = threadIdx.x; w * 32u < nbits; w += blockDim.x) {
+			u32 out = 0;
+			for (u32 b = 0; b < 32; b++) {
+				u32 x = w * 32u + b;
+				if (x >= nbits) break;
+				u32 up = 4u * x;
+				if ((upper[up >> 5] >> (up & 31u)) & 0xfu) out |= 1u << b;
+			}
+			lower[w] = out;
+		}
+		__syncthreads();  // the next level reads what this one wrote (same CTA: visible after the barrier)
+	}
+}
+
 // Positions [first, first + count) are examined (all of the text when separators may be anywhere,
 // just the K positions in front of '#' and of the text end otherwise).
 __global__ void k_presence_patch(TextView rs, int K, PresenceLevels lv, u32 first, u32 count) {

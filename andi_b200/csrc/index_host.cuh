@@ -159,10 +159,11 @@ static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
 	cudaStream_t st = ctx->stream;
 	const int K = E->K;
 	TextView rs = rs_view(E);
-	for (int m = K - 2; m >= 1; m--) {
-		u32 nb = 1u << (2 * m);
-		k_presence_down<<<nblocks((nb + 31) / 32, 256), 256, 0, st>>>(E->present.bits + E->present.offset[m + 1], nb,
-																	   E->present.bits + E->present.offset[m]);
+	if (K >= 3) {  // level K-2 by the whole grid, everything below it by one CTA
+		u32 nb = 1u << (2 * (K - 2));
+		k_presence_down<<<nblocks((nb + 31) / 32, 256), 256, 0, st>>>(E->present.bits + E->present.offset[K - 1], nb,
+																	   E->present.bits + E->present.offset[K - 2]);
+		if (K >= 4) k_presence_down_all<<<1, 1024, 0, st>>>(E->present, K - 2);
 	}
 	if (E->has_sep) {
 		k_presence_patch<<<nblocks(E->N, 256), 256, 0, st>>>(rs, K, E->present, 0, E->N);
@@ -173,7 +174,7 @@ static int build_prefix_lengths(andi_ctx *ctx, andi_esa *E) {
 		k_presence_patch<<<1, 32, 0, st>>>(rs, K, E->present, E->N >= k ? E->N - k : 0, k + 1);
 	}
 	k_prefix_len<<<nblocks((size_t)1 << (2 * (K - 1)), 256), 256, 0, st>>>(E->present, K, E->dir, E->SA, E->code, E->plen, E->fdir);
-	ctx->st.esa_launches += 3 + (K - 2);
+	ctx->st.esa_launches += 3 + (K >= 4 ? 2 : (K >= 3 ? 1 : 0));
 	return ANDI_OK;
 }
 

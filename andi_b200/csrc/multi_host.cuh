@@ -29,9 +29,12 @@ extern "C" int andi_pool_import(andi_ctx *ctx, const andi_pool_view *v, int src_
 	const void *src_code = v->d_code, *src_spec = v->d_spec;
 	const bool any = v->any_separator != 0;
 	if (src_code == ctx->pool_code) return ANDI_OK;	 // importing one's own pool
-	u64 *code = nullptr, *spec = nullptr;
-	CK(dalloc(ctx, &code, words));
-	CK(dalloc(ctx, &spec, words));
+	pool_release(ctx);
+	{
+		int rc2 = planes_ensure(ctx, words);
+		if (rc2) return rc2;
+	}
+	u64 *code = ctx->pool_code, *spec = ctx->pool_spec;
 	const size_t bytes = words * sizeof(u64);
 	if (src_device < 0 || src_device == ctx->device) {
 		CK(cudaMemcpyAsync(code, src_code, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -47,8 +50,6 @@ extern "C" int andi_pool_import(andi_ctx *ctx, const andi_pool_view *v, int src_
 	}
 	if (!(any && src_spec)) CK(cudaMemsetAsync(spec, 0, bytes, ctx->stream));  // a pool without separators: nothing to move
 	CK(cudaStreamSynchronize(ctx->stream));
-	pool_release(ctx);
-	ctx->pool_code = code, ctx->pool_spec = spec, ctx->pool_words = words;
 	ctx->n = n, ctx->len = len, ctx->gc = gc, ctx->has_sep = has_sep, ctx->any_sep = any;
 	ctx->word_off.resize(n);
 	std::vector<QueryView> qv(n);

@@ -358,12 +358,13 @@ def main():
             else:
                 ctx2._ck(L.andi_dist_rows(ctx2.h, s0, s0 + rows, 0.025, native.MODELS[model], 0, C.c_void_p(out_host.data_ptr())))
 
-        step_e2e(0)
+        for w in range(args.warmup):
+            step_e2e(w)
         barrier()
         ctx2.reset_stats()
         e0.record(stream)
         for s in range(args.steps):
-            step_e2e(1 + s)
+            step_e2e(args.warmup + s)
         e1.record(stream)
         barrier()
         ms2 = max_over_ranks(e0.elapsed_time(e1))
