@@ -48,7 +48,20 @@ static inline u32 v3_kmer_key(u64 win, int k) {
 	return key;
 }
 
+struct V3Lane;
+struct V3Const;
+static inline void v3_count_slice(const V3Lane &L, const V3Const &c, u32 *col, u32 sign);
+
 #include "../walk_v3_lane.h"
+
+// model.c:259-278 by counting the characters of the query slice (the kernel uses the pool's
+// prefix-composition table; the emulation has no such table and does not need the speed)
+static inline void v3_count_slice(const V3Lane &L, const V3Const &, u32 *col, u32 sign) {
+	for (u32 x = 0; x < L.ll; x++) {
+		const u32 q = (u32)(L.q_code[(L.lq + x) >> 5] >> (((L.lq + x) & 31u) * 2u)) & 3u;
+		col[q * 5u] += sign;
+	}
+}
 
 static inline u32 code_at(const u64 *w, u32 pos) { return (u32)(w[pos >> 5] >> ((pos & 31u) * 2u)) & 3u; }
 
@@ -106,6 +119,7 @@ struct Env {
 		return v3_begin_unit<PHASE>(L, c, pool_code + q_off[k], q_len[k], ch, records + unit * ANDI_UNIT_WORDS, col);
 	}
 	// one iteration of src/process.c:153-197 in the generic form (walk_step of walk_kernels.cuh)
+	template <bool QUARTER>
 	void slow_step(V3Lane &L, u32 *col, u32 sign) {
 		V3_STAT(slow_steps);
 		V3_STAT(steps);
@@ -128,7 +142,14 @@ struct Env {
 		if (found) {
 			u32 end_s = L.ls + L.ll, end_q = L.lq + L.ll;
 			bool pairs = cur_s > end_s && (L.pos - end_q) == (cur_s - end_s) && ((cur_s < border) == (L.ls < border));
-			if (pairs || L.paired || L.ll >= 2 * t) L.sumq += (L.ll >> 2) * sign, L.sumr += (L.ll & 3u) * sign;
+			if (pairs || L.paired || L.ll >= 2 * t) {
+				if (QUARTER) {
+					L.sumq += (L.ll >> 2) * sign, L.sumr += (L.ll & 3u) * sign;
+				} else {
+					V3Const none{};
+					v3_count_slice(L, none, col, sign);
+				}
+			}
 			if (pairs)
 				for (u32 x = 0; x < L.pos - end_q; x++) {
 					if (end_s + x == h.mid) continue;
@@ -142,7 +163,7 @@ struct Env {
 	u32 c_t;
 };
 
-template <int PHASE>
+template <int PHASE, bool QUARTER>
 static void run_phase(Env &env, const V3Const &c, u32 n_warps) {
 	struct Warp {
 		V3Lane lane[32];
@@ -171,7 +192,7 @@ static void run_phase(Env &env, const V3Const &c, u32 n_warps) {
 			if (v3_serve_now(parked, running, w.trip)) {
 				if (g_stats) g_stats[ST_services]++, g_stats[ST_served_lanes] += parked;
 				for (u32 x = 0; x < 32; x++)
-					if (w.lane[x].svc != V3_RUN && w.lane[x].svc != V3_SVC_DONE) v3_service<PHASE>(w.lane[x], c, env, w.cells[x], w.pend(x));
+					if (w.lane[x].svc != V3_RUN && w.lane[x].svc != V3_SVC_DONE) v3_service<PHASE, QUARTER>(w.lane[x], c, env, w.cells[x], w.pend(x));
 			}
 			u32 most = 0;
 			for (auto &l : w.lane) most = l.npend > most ? l.npend : most;
@@ -181,7 +202,7 @@ static void run_phase(Env &env, const V3Const &c, u32 n_warps) {
 			}
 			running = 0;
 			for (u32 x = 0; x < 32; x++)
-				if (w.lane[x].svc == V3_RUN) running++, v3_trip<PHASE>(w.lane[x], c, w.cells[x], w.pend(x));
+				if (w.lane[x].svc == V3_RUN) running++, v3_trip<PHASE, QUARTER>(w.lane[x], c, w.cells[x], w.pend(x));
 			if (g_stats && running) g_stats[ST_warp_trips]++, g_stats[ST_running_lanes] += running;
 			w.trip++;
 		}
@@ -193,7 +214,7 @@ extern "C" int emu_v3_stats(void) { return ST_N; }
 // Both launches (PHASE 1 then PHASE 2) for one subject. Returns 0, or -1 on bad arguments.
 extern "C" long emu_walk_v3(const u64 *s_code, u32 N, u32 mid, const u32 *SA, const u64 *fdir, int K, u32 self, u32 threshold,
 							const u64 *pool_code, const u64 *q_word_off, const u32 *q_len, u32 nq, u32 chunk, u32 cpq,
-							u32 *records, u64 *stats, u32 n_warps) {
+							u32 *records, u64 *stats, u32 n_warps, int quarter) {
 	if (!s_code || !SA || !fdir || !pool_code || !records || threshold > V3_MAX_T || K > (int)threshold || (int)threshold > K + 15 || n_warps == 0) return -1;
 	V3Const c;
 	c.t = threshold, c.N = N, c.mid = mid, c.border = N / 2, c.chunk = chunk, c.cpq = cpq, c.K = K, c.s_code = s_code, c.fdir = fdir, c.SA = SA;
@@ -202,9 +223,16 @@ extern "C" long emu_walk_v3(const u64 *s_code, u32 N, u32 mid, const u32 *SA, co
 	env.total = (u64)nq * cpq, env.records = records, env.pool_code = pool_code, env.q_off = q_word_off, env.q_len = q_len;
 	env.self = self, env.nq = nq, env.c_t = threshold;
 	g_stats = stats;
-	run_phase<1>(env, c, n_warps);
+	c.qcode_base = nullptr, c.qcomp_base = nullptr;
+	if (quarter)
+		run_phase<1, true>(env, c, n_warps);
+	else
+		run_phase<1, false>(env, c, n_warps);
 	g_stats = stats ? stats + ST_N : nullptr;
-	run_phase<2>(env, c, n_warps);
+	if (quarter)
+		run_phase<2, true>(env, c, n_warps);
+	else
+		run_phase<2, false>(env, c, n_warps);
 	g_stats = nullptr;
 	return 0;
 }

@@ -20,12 +20,14 @@ static void pick_walk(int model, bool spec, chunks_fn &cf, reduce_fn &rf) {
 	if (!quarter && !spec) cf = k_walk_chunks<false, false>, rf = k_walk_reduce<false, false>;
 }
 
-// Chunk length: aim at ~8 units per resident thread so the grid-stride loop balances, keep
-// chunks long enough that the boundary replay (a handful of steps) stays a small fraction.
+// Chunk length: aim at ~5 units per resident thread so the dynamic unit queue balances, keep chunks
+// long enough that the boundary replay (a handful of steps) and the per-unit record stay a small
+// fraction.
 static u32 pick_chunk(const andi_ctx *ctx, unsigned long long total_bases) {
-	unsigned long long target_units = (unsigned long long)ctx->sm_count * 1024ULL * 8ULL;
+	unsigned long long target_units = (unsigned long long)ctx->sm_count * 1024ULL * 11ULL / 2ULL;
 	unsigned long long want = total_bases / target_units;
-	// measured on the C4 shape: 2048 -> 310 k, 4096 -> 341 k, 5120 -> 345 k, 8192 -> 334 k, 16384 -> 315 k pairs/s
+	// measured on the C4 shape, round 1 (phase pipeline): 2048 -> 310 k, 4096 -> 341 k, 5120 -> 345 k, 8192 -> 334 k pairs/s;
+	// round 2 (k_walk_v3, two subjects in flight): 4096 -> 519 k, 5632 -> 536 k, 8192 -> 546 k, 11264 -> 544 k
 	u32 chunk = (u32)std::min<unsigned long long>(16384ULL, std::max<unsigned long long>(1024ULL, (want + 511ULL) / 512ULL * 512ULL));
 	const char *env = getenv("ANDI_B200_CHUNK");
 	if (env && atoi(env) >= 64) chunk = (u32)atoi(env);
@@ -102,11 +104,13 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	}
 	// the headline configuration goes through k_walk_v3 (walk_v3.cuh): PHASE 1 over all units,
 	// PHASE 2 over all chunk boundaries; ANDI_B200_WALK=pipeline keeps the round-1 kernel
-	const bool v3 = quarter && !spec && v3_applies(S, threshold) && !(force && (strcmp(force, "basic") == 0 || strcmp(force, "pipeline") == 0));
+	// (LOGDET / ANI: only pool queries have the prefix-composition table the anchor interiors need)
+	const bool v3 = !spec && (quarter || (pool_queries && S.qcomp_base)) && v3_applies(S, threshold) &&
+					!(force && (strcmp(force, "basic") == 0 || strcmp(force, "pipeline") == 0));
 	int per_sm = 0;
 	const unsigned threads = v3 ? V3_THREADS : ANDI_WALK_THREADS;
 	if (v3)
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_v3<1>, V3_THREADS, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quarter ? k_walk_v3<1, true> : k_walk_v3<1, false>, V3_THREADS, 0));
 	else
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf, ANDI_WALK_THREADS, 0));
 	if (per_sm < 1) per_sm = 1;
@@ -121,11 +125,12 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	if (!ctx->walk_counter) CK(dalloc(ctx, &ctx->walk_counter, 2));
 	CK(cudaMemsetAsync(ctx->walk_counter, 0, 2 * sizeof(unsigned long long), ctx->stream));
 	if (v3) {
-		k_walk_v3<1><<<grid, V3_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
-																   d_records, ctx->walk_counter);
+		auto p1 = quarter ? k_walk_v3<1, true> : k_walk_v3<1, false>;
+		auto p2 = quarter ? k_walk_v3<2, true> : k_walk_v3<2, false>;
+		p1<<<grid, V3_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records, ctx->walk_counter);
 		if (plan.cpq > 1)
-			k_walk_v3<2><<<grid, V3_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
-																	   d_records, ctx->walk_counter + 1);
+			p2<<<grid, V3_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records,
+													 ctx->walk_counter + 1);
 		ctx->st.walk_launches += plan.cpq > 1 ? 1 : 0;
 	} else {
 		cf<<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,

@@ -1,5 +1,5 @@
-// andi_b200/csrc/walk_v3.cuh -- k_walk_v3<PHASE>: the chunked anchor walk for RAW / JC / KIMURA
-// counting without separators (the headline configuration). The per-lane logic, its rationale and
+// andi_b200/csrc/walk_v3.cuh -- k_walk_v3<PHASE, QUARTER>: the chunked anchor walk for texts without
+// separators (QUARTER = RAW / JC / KIMURA counting, the headline configuration; else LOGDET / ANI). The per-lane logic, its rationale and
 // its reference citations are in walk_v3_lane.h (the same text runs in the CPU emulation of
 // emu/emu_v3.cpp); this file supplies the device primitives, the warp loop and the launch.
 //
@@ -36,7 +36,26 @@ V3_FN u32 v3_ld_sa(const u32 *p) { return __ldg(p); }
 V3_FN void v3_window64(const u64 *__restrict__ w, u32 pos, u64 &lo, u64 &hi) { window64(w, pos, lo, hi); }
 V3_FN u32 v3_kmer_key(u64 win, int k) { return kmer_key(win, k); }
 
+struct V3Lane;
+struct V3Const;
+V3_FN void v3_count_slice(const V3Lane &L, const V3Const &c, u32 *col, u32 sign);
+
 #include "walk_v3_lane.h"
+
+// model.c:259-278 in O(1): the composition of the query slice [lq, lq + ll) from the per-word prefix
+// composition of the pool (k_comp_prefix): two table entries and the two partial words at the ends.
+V3_FN void v3_count_slice(const V3Lane &L, const V3Const &c, u32 *col, u32 sign) {
+	const uint4 *cp = reinterpret_cast<const uint4 *>(c.qcomp_base) + (L.q_code - c.qcode_base);
+	const u32 b0 = L.lq, b1 = L.lq + L.ll;
+	const uint4 p0 = __ldg(cp + (b0 >> 5)), p1 = __ldg(cp + (b1 >> 5));
+	const u64 w0 = __ldg(L.q_code + (b0 >> 5)), w1 = __ldg(L.q_code + (b1 >> 5));
+	const u64 m0 = ANDI_EVEN_BITS & ((1ULL << (2u * (b0 & 31u))) - 1ULL), m1 = ANDI_EVEN_BITS & ((1ULL << (2u * (b1 & 31u))) - 1ULL);
+	const u64 l0 = w0 & m0, h0 = (w0 >> 1) & m0, l1 = w1 & m1, h1 = (w1 >> 1) & m1;
+	col[0 * V3_CELL_STRIDE] += (p1.x - p0.x + (u32)__popcll(m1 & ~l1 & ~h1) - (u32)__popcll(m0 & ~l0 & ~h0)) * sign;
+	col[5 * V3_CELL_STRIDE] += (p1.y - p0.y + (u32)__popcll(l1 & ~h1) - (u32)__popcll(l0 & ~h0)) * sign;
+	col[10 * V3_CELL_STRIDE] += (p1.z - p0.z + (u32)__popcll(h1 & ~l1) - (u32)__popcll(h0 & ~l0)) * sign;
+	col[15 * V3_CELL_STRIDE] += (p1.w - p0.w + (u32)__popcll(h1 & l1) - (u32)__popcll(h0 & l0)) * sign;
+}
 
 struct V3Acc {	// the count cells of this lane, as walk_step<> wants them
 	u32 *col;
@@ -46,6 +65,7 @@ struct V3Acc {	// the count cells of this lane, as walk_step<> wants them
 
 // The generic step (walk_step of walk_kernels.cuh) for the few lanes the window jobs do not
 // cover; a real call, so its registers do not weigh on the main loop.
+template <bool QUARTER>
 __device__ __noinline__ void v3_slow_step(const SubjectIndex &S, u32 t, const u64 *q_code, u32 qlen, u32 *col, u32 sign,
 										  u32 &pos, u32 &ls, u32 &lq, u32 &ll, u32 &paired) {
 	TextView q;
@@ -53,7 +73,7 @@ __device__ __noinline__ void v3_slow_step(const SubjectIndex &S, u32 t, const u6
 	WalkState w;
 	w.pos_q = pos, w.last_s = ls, w.last_q = lq, w.last_len = ll, w.paired = paired;
 	V3Acc acc = {col, sign};
-	walk_step<true, false>(S, q, t, w, acc);
+	walk_step<QUARTER, false>(S, q, t, w, acc);
 	pos = w.pos_q, ls = w.last_s, lq = w.last_q, ll = w.last_len, paired = w.paired;
 }
 
@@ -74,15 +94,16 @@ struct V3Env {
 		if (qid == S.self) return false;
 		return v3_begin_unit<PHASE>(L, c, queries[qid].t.code, queries[qid].t.len, ch, records + unit * ANDI_UNIT_WORDS, col);
 	}
+	template <bool QUARTER>
 	__device__ __forceinline__ void slow_step(V3Lane &L, u32 *col, u32 sign) {
 		// (copies: a lane field whose address escapes into the call would live in local memory)
 		u32 pos = L.pos, ls = L.ls, lq = L.lq, ll = L.ll, paired = L.paired;
-		v3_slow_step(S, t, L.q_code, L.qlen, col, sign, pos, ls, lq, ll, paired);
+		v3_slow_step<QUARTER>(S, t, L.q_code, L.qlen, col, sign, pos, ls, lq, ll, paired);
 		L.pos = pos, L.ls = ls, L.lq = lq, L.ll = ll, L.paired = paired;
 	}
 };
 
-template <int PHASE>
+template <int PHASE, bool QUARTER>
 __global__ void __launch_bounds__(V3_THREADS, V3_BLOCKS_PER_SM)
 k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 nq, u32 chunk,
 		  u32 cpq, u32 threshold, u32 *__restrict__ records, unsigned long long *__restrict__ next_unit) {
@@ -93,7 +114,7 @@ k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32
 	const V3Pend P = {&pend_q[0][threadIdx.x], &pend_s[0][threadIdx.x], &pend_g[0][threadIdx.x]};
 	V3Const c;
 	c.t = threshold, c.N = S.rs.len, c.mid = S.rs.mid, c.border = S.rs.len / 2, c.chunk = chunk, c.cpq = cpq, c.K = S.K;
-	c.s_code = S.rs.code, c.fdir = S.fdir, c.SA = S.SA;
+	c.s_code = S.rs.code, c.fdir = S.fdir, c.SA = S.SA, c.qcode_base = S.qcode_base, c.qcomp_base = S.qcomp_base;
 	V3Env env = {S, (u64)nq * cpq, records, next_unit, queries, query_ids, threshold};
 	V3Lane L;
 	L.svc = V3_SVC_FETCH, L.job = V3_STEP;
@@ -105,7 +126,7 @@ k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32
 		const unsigned running = __ballot_sync(0xffffffffu, L.svc == V3_RUN);
 		if (!(parked | running)) break;
 		if (v3_serve_now((u32)__popc(parked), (u32)__popc(running), trip)) {
-			if (L.svc != V3_RUN && L.svc != V3_SVC_DONE) v3_service<PHASE>(L, c, env, col, P);
+			if (L.svc != V3_RUN && L.svc != V3_SVC_DONE) v3_service<PHASE, QUARTER>(L, c, env, col, P);
 			__syncwarp();
 		}
 		if (__any_sync(0xffffffffu, L.npend > V3_PEND_SLOTS - 2u)) {
@@ -117,7 +138,7 @@ k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32
 			}
 			L.npend = 0;
 		}
-		if (L.svc == V3_RUN) v3_trip<PHASE>(L, c, col, P);
+		if (L.svc == V3_RUN) v3_trip<PHASE, QUARTER>(L, c, col, P);
 		__syncwarp();
 	}
 }

@@ -27,7 +27,8 @@
 //    of them wait (or every few trips), so the rare code runs with several lanes instead of one.
 //    The slow step itself is walk_step<>() of walk_kernels.cuh, the proven generic form.
 //
-// QUARTER (RAW / JC / KIMURA) without separators only; the other three instantiations stay with
+// Texts without separators only (RAW / JC / KIMURA, and LOGDET / ANI for pool queries: their
+// anchor interiors need the pool's prefix-composition table); join mode stays with
 // k_walk_chunks_fast.
 #pragma once
 
@@ -51,6 +52,10 @@ struct V3Const {
 	const u64 *s_code;
 	const u64 *fdir;
 	const u32 *SA;
+	// LOGDET / ANI only: base of the pool's code plane and of its prefix-composition table (same
+	// word geometry, k_comp_prefix): comp = qcomp_base + (q_code - qcode_base)
+	const u64 *qcode_base;
+	const void *qcomp_base;
 };
 
 // Chain A is the one being advanced. PHASE 2 carries a second chain B and `a_true` (A is the
@@ -121,7 +126,7 @@ V3_FN u32 v3_first_diff(u64 x0, u64 x1) {
 
 // One trip of a running lane (L.svc == V3_RUN). `col` = this lane's column of the count cells
 // (cell x at col[x * V3_CELL_STRIDE]). On entry L.npend <= V3_PEND_SLOTS - 2.
-template <int PHASE>
+template <int PHASE, bool QUARTER>
 V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	const u32 t = c.t;
 	u32 sign = 1u;
@@ -287,9 +292,13 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 		V3_STAT(steps);
 		if (is_step) V3_STAT(lucky_hits);
 		const bool pairs = cur_s > end_s && (L.pos - end_q) == (cur_s - end_s) && ((cur_s < c.border) == (L.ls < c.border));
-		if (pairs || L.paired || L.ll >= 2u * t) {	// model.c:247-254 for the previous anchor
-			L.sumq += (L.ll >> 2) * sign;
-			L.sumr += (L.ll & 3u) * sign;
+		if (pairs || L.paired || L.ll >= 2u * t) {	// the previous anchor's interior
+			if (QUARTER) {	// model.c:247-254 (RAW / JC / KIMURA): a quarter to each diagonal cell, remainder to TtoT
+				L.sumq += (L.ll >> 2) * sign;
+				L.sumr += (L.ll & 3u) * sign;
+			} else {  // model.c:259-278 (LOGDET / ANI): the composition of the query slice
+				v3_count_slice(L, c, col, sign);
+			}
 		}
 		L.ls = cur_s, L.lq = L.pos, L.ll = matched, L.paired = pairs ? 1u : 0u;
 		if (complete_a) L.pos += matched + 1u;
@@ -382,7 +391,7 @@ V3_FN void v3_finish_unit(const V3Lane &L, u32 *rec, const u32 *col) {
 // Serve one parked lane. Env supplies what differs between the kernel and the emulation:
 //   u64 total; u32 *records; u64 next_unit(); bool open_unit(u64 unit, V3Lane &, u32 *&rec)  (query lookup +
 //   v3_begin_unit; false = no work in this unit); void slow_step(V3Lane &, u32 *col, u32 sign).
-template <int PHASE, class Env>
+template <int PHASE, bool QUARTER, class Env>
 V3_FN void v3_service(V3Lane &L, const V3Const &c, Env &env, u32 *col, const V3Pend &P) {
 	if (L.svc == V3_SVC_SCAN) {
 		// a bucket of three or more suffixes (L.cand_p = first SA index, L.cand2 = their number):
@@ -413,7 +422,7 @@ V3_FN void v3_service(V3Lane &L, const V3Const &c, Env &env, u32 *col, const V3P
 		L.svc = V3_SVC_SLOW;
 	}
 	if (L.svc == V3_SVC_SLOW) {
-		env.slow_step(L, col, (PHASE == 2 && !L.a_true) ? 0xffffffffu : 1u);
+		env.template slow_step<QUARTER>(L, col, (PHASE == 2 && !L.a_true) ? 0xffffffffu : 1u);
 		L.svc = V3_RUN;
 		return;
 	}

@@ -32,10 +32,10 @@ def _assert_rows(got, want, what):
 def test_c4_shape(ctx, monkeypatch):
     """Config 4 as benched: 2.1 Mbp genomes, d_k ~ U[0.005, 0.02], JC, directory depth 12 (what
     choose_depth picks once a subject is walked by a gigabase of queries) and the chunk length the
-    3085-genome pool gets (5632)."""
+    3085-genome pool gets (8192)."""
     _need_ref()
     monkeypatch.setenv("ANDI_B200_DEPTH_BIAS", "1")
-    monkeypatch.setenv("ANDI_B200_CHUNK", "5632")
+    monkeypatch.setenv("ANDI_B200_CHUNK", "8192")
     n = 8
     seqs = synth.star_phylogeny(n, 2_100_000, synth.config_divergences(n, 0.005, 0.02, 3085), seed=3085)
     want, _ = oracle.ref_rows(seqs, "JC", threads=8)

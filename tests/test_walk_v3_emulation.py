@@ -33,7 +33,7 @@ def load_emu():
     L = C.CDLL(str(so))
     L.emu_walk_v3.restype = C.c_long
     L.emu_walk_v3.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
-                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
     assert L.emu_v3_stats() == len(STATS)
     return L
 
@@ -101,9 +101,10 @@ def directory_view(rs: bytes, SA: np.ndarray, K: int) -> np.ndarray:
     return fdir
 
 
-def reduce_records(rec: np.ndarray, qlens, chunk: int, cpq: int, threshold: int, skip: int) -> np.ndarray:
+def reduce_records(rec: np.ndarray, qlens, chunk: int, cpq: int, threshold: int, skip: int, quarter: bool = True, queries=None) -> np.ndarray:
     """k_walk_reduce for records whose boundaries all synchronised, plus walk_tail
-    (src/process.c:199-211) with the len/4 split of src/model.c:247-254."""
+    (src/process.c:199-211): the last anchor's interior by the len/4 split of src/model.c:247-254
+    (RAW / JC / KIMURA) or by the composition of its query slice (src/model.c:259-278)."""
     out = np.zeros((len(qlens), 17), dtype=np.uint32)
     for k, qlen in enumerate(qlens):
         if k == skip:
@@ -113,18 +114,22 @@ def reduce_records(rec: np.ndarray, qlens, chunk: int, cpq: int, threshold: int,
         r = rec[k * cpq : k * cpq + nch].astype(np.int64)
         assert (r[:-1, 37] == 1).all(), "a chunk boundary did not synchronise: needs the sequential path of k_walk_reduce"
         total = r[:, :16].sum(axis=0) + r[:-1, 16:32].astype(np.int32).sum(axis=0)
-        last_len, paired = int(r[-1, 35]), int(r[-1, 36])
-        tail = qlen if last_len >= qlen else (last_len if (paired or last_len >= 2 * threshold) else 0)
-        for cell in (0, 5, 10):
-            total[cell] += tail // 4
-        total[15] += tail // 4 + tail % 4
+        last_q, last_len, paired = int(r[-1, 34]), int(r[-1, 35]), int(r[-1, 36])
+        start, tail = (0, qlen) if last_len >= qlen else ((last_q, last_len) if (paired or last_len >= 2 * threshold) else (0, 0))
+        if quarter:
+            for cell in (0, 5, 10):
+                total[cell] += tail // 4
+            total[15] += tail // 4 + tail % 4
+        else:
+            comp = np.bincount(CODE[np.frombuffer(queries[k][start : start + tail], dtype=np.uint8)], minlength=4)
+            for b in range(4):
+                total[5 * b] += int(comp[b])
         out[k, :16] = total.astype(np.uint32)
         out[k, 16] = qlen
     return out
 
 
-
-def emulate_rows(emu, seqs, chunk, warps=3, stats=None):
+def emulate_rows(emu, seqs, chunk, warps=3, stats=None, model="JC"):
     """All rows of the matrix through the emulation; returns (rows, per-phase statistics)."""
     qplanes = [pack(s) for s in seqs]
     q_off = np.cumsum([0] + [len(p) for p in qplanes[:-1]]).astype(np.uint64)
@@ -143,10 +148,12 @@ def emulate_rows(emu, seqs, chunk, warps=3, stats=None):
         rec = np.zeros((len(seqs) * cpq, UNIT_WORDS), dtype=np.uint32)
         st = np.zeros(2 * len(STATS), dtype=np.uint64)
         rc = emu.emu_walk_v3(s_code.ctypes.data, N, N // 2, SA.ctypes.data, fdir.ctypes.data, K, i, t, pool.ctypes.data,
-                             q_off.ctypes.data, q_len.ctypes.data, len(seqs), chunk, cpq, rec.ctypes.data, st.ctypes.data, warps)
+                             q_off.ctypes.data, q_len.ctypes.data, len(seqs), chunk, cpq, rec.ctypes.data, st.ctypes.data, warps,
+                             int(model in ("RAW", "JC", "KIMURA")))
         assert rc == 0
         total += st
-        rows[i] = reduce_records(rec, [int(x) for x in q_len], chunk, cpq, t, skip=i)
+        rows[i] = reduce_records(rec, [int(x) for x in q_len], chunk, cpq, t, skip=i, quarter=model in ("RAW", "JC", "KIMURA"),
+                                 queries=seqs)
         o.close()
     n = len(STATS)
     return rows, {"phase1": dict(zip(STATS, total[:n].tolist())), "phase2": dict(zip(STATS, total[n:].tolist()))}
@@ -157,11 +164,11 @@ def emulate_rows(emu, seqs, chunk, warps=3, stats=None):
 @pytest.mark.parametrize("name,chunk", [("subst", 1000), ("subst", 4096), ("indel", 700), ("repeat", 1 << 20),
                                         ("identical", 1 << 20), ("lowent", 1 << 20), ("short", 1 << 20), ("unrelated", 1 << 20),
                                         ("revcomp", 2048)])
-@pytest.mark.parametrize("warps", [1, 5])
-def test_v3_lane_logic_matches_the_oracle(emu, name, chunk, warps):
+@pytest.mark.parametrize("warps,model", [(1, "JC"), (5, "JC"), (3, "LOGDET")])
+def test_v3_lane_logic_matches_the_oracle(emu, name, chunk, warps, model):
     from conftest import stress_sequences
 
     seqs = [s for s in stress_sequences()[name] if b"!" not in s]
-    want = oracle.rows(seqs, "JC")
-    got, stats = emulate_rows(emu, seqs, chunk, warps)
-    assert np.array_equal(got, want), (name, chunk, warps, stats)
+    want = oracle.rows(seqs, model)
+    got, stats = emulate_rows(emu, seqs, chunk, warps, model=model)
+    assert np.array_equal(got, want), (name, chunk, warps, model, stats)

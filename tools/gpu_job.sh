@@ -1,9 +1,6 @@
 #!/bin/bash
-# 2 GPUs: multi-device tests, then the bench at N=2
-python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -6
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2j_bench_n2.json 2> gpurun_out/r2j_bench_n2.err
-tail -3 gpurun_out/r2j_bench_n2.err
-python - <<'PY'
-import json
-d=json.load(open("gpurun_out/r2j_bench_n2.json")); print("n2", d["value"], d["ms_per_step"], d["e2e"], d["full_matrix"])
-PY
+python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/r2k_gpu_tests.log 2>&1
+tail -15 gpurun_out/r2k_gpu_tests.log | cut -c1-200
+for m in KIMURA LOGDET; do python bench.py --workload c3 --model $m --steps 3 --warmup 3 --no-cpu --no-e2e --no-full --rows 109 2>/dev/null | python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('c3 $m', d['value'], d['ms_per_step'], d['esa_build']['ms_per_subject'], d['roofline']['launch_ms'], d['cub_calls'])"; done
+ANDI_B200_WALK=pipeline python bench.py --workload c3 --model LOGDET --steps 3 --warmup 3 --no-cpu --no-e2e --no-full --rows 109 2>/dev/null | python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('c3 LOGDET pipeline kernel', d['value'], d['ms_per_step'])"
+python bench.py --model LOGDET --steps 2 --warmup 2 --no-cpu --no-e2e --no-full 2>/dev/null | python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('c4 LOGDET', d['value'], d['roofline']['launch_ms'])"
