@@ -381,7 +381,9 @@ rebuild:
 		// deep directory, no separators: own two-level counting sort (sa_bucket.cuh)
 		const int K2 = K / 2, K1 = K - K2;
 		const u32 parts = 1u << (2 * K1), bins = 1u << (2 * K2);
-		const unsigned ctas = (unsigned)ctx->sm_count * 2u;
+		// one CTA per SM: every CTA keeps one open write sector per part, and 148 x 16384 x 32 B has to stay in L2
+		const char *pc = getenv("ANDI_B200_PART_CTAS");	 // experiments
+		const unsigned ctas = (unsigned)ctx->sm_count * (pc && atoi(pc) == 2 ? 2u : 1u);
 		const u32 per_cta = (N + ctas - 1) / ctas;
 		static bool attr_set = false;
 		if (!attr_set) {

@@ -72,26 +72,6 @@ __device__ __forceinline__ bool is_padded(const TextView &rs, u32 p, int K) {
 	return p + (u32)K > rs.len || (p <= rs.mid && rs.mid < p + (u32)K);
 }
 
-// Large texts: the histogram / cursor tables no longer fit in L2 and the atomics above turn into
-// random DRAM traffic. There the bucketing pass is a library radix sort of (key, position)
-// pairs (cub::DeviceRadixSort, 2K key bits) and the bucket bounds are read off the sorted keys
-// -- sequential writes, because the keys ascend.
-__global__ void k_bucket_keys(TextView rs, int K, u32 *__restrict__ keys, u32 *__restrict__ idx) {
-	u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= rs.len) return;
-	u32 run;
-	keys[i] = padded_key(rs, i, K, run);
-	idx[i] = i;
-}
-
-__global__ void k_bucket_bounds(const u32 *__restrict__ keys, u32 N, u32 *__restrict__ bstart, u32 *__restrict__ bend) {
-	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= N) return;
-	u32 k = keys[j];
-	if (j == 0 || keys[j - 1] != k) bstart[k] = j;
-	if (j + 1 == N || keys[j + 1] != k) bend[k] = j + 1;
-}
-
 // ---- texts with separators ('!' / ';' of join mode): the padded suffixes.
 // Every suffix with a separator (or the text end) inside its first K characters has a padded
 // key, and they pile up: all suffixes that START with a separator share key 0, a genome of
@@ -386,8 +366,9 @@ __global__ void k_bucket_sort_slots(TextView rs, int K, u32 *__restrict__ SA, u6
 // (2) its threads wait for the sums of all CTAs before it and add them up -- everybody is resident,
 // so nobody waits for a CTA that cannot run --, (3) it scans its stretch tile by tile.
 // out[k] = number of suffixes in buckets < k (may alias hist: the histogram becomes the scatter
-// cursor), out[n] = N. With dir64 given, the directory entries of EMPTY buckets are written on
-// the way (first = end of the bucket, count 0): k_bucket_sort_slots never sees those buckets.
+// cursor), out[n] = N. With dir64 given, the directory is initialised on the way: the entries of
+// EMPTY buckets are final (first = end of the bucket, count 0) -- k_bucket_sort_slots never sees
+// those buckets --, the others are rewritten by the bucket sort.
 #define ANDI_SCAN_TILE 4096u  // 256 threads x 16 keys
 __device__ __forceinline__ u32 block_sum_256(u32 v, u32 *warp_sum) {
 	for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -469,10 +450,19 @@ __global__ void __launch_bounds__(256) k_scan_buckets(const u32 *hist, u32 n, u3
 			if (base + 2u < b1) out[base + 2u] = r2;
 		}
 		if (dir64) {
-			if (base + 0u < b1 && x.x == 0u) dir64[base + 0u] = (u64)r0;
-			if (base + 1u < b1 && x.y == 0u) dir64[base + 1u] = (u64)r1;
-			if (base + 2u < b1 && x.z == 0u) dir64[base + 2u] = (u64)r2;
-			if (base + 3u < b1 && x.w == 0u) dir64[base + 3u] = (u64)r3;
+			// every entry, as full 32-byte stores (predicated 8-byte stores to the empty ones alone made
+			// partial sectors: 190 MB read + 160 MB written for a 134 MB table). An empty bucket's
+			// entry is final (first = its end, count 0); a non-empty one gets first | count here and
+			// is rewritten by the bucket sort with the count of suffixes that really carry the k-mer.
+			if (base + 3u < b1) {
+				ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dir64 + base);
+				d[0] = make_ulonglong2((u64)r0 | ((u64)x.x << 32), (u64)r1 | ((u64)x.y << 32));
+				d[1] = make_ulonglong2((u64)r2 | ((u64)x.z << 32), (u64)r3 | ((u64)x.w << 32));
+			} else {
+				if (base + 0u < b1) dir64[base + 0u] = (u64)r0 | ((u64)x.x << 32);
+				if (base + 1u < b1) dir64[base + 1u] = (u64)r1 | ((u64)x.y << 32);
+				if (base + 2u < b1) dir64[base + 2u] = (u64)r2 | ((u64)x.z << 32);
+			}
 		}
 		run0 += tile_total;
 	}

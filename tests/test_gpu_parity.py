@@ -315,3 +315,20 @@ def test_randomised_pools(ctx, seed, monkeypatch):
         want = oracle.rows(seqs, model)
         bad = np.argwhere((got != want).any(axis=2))
         assert len(bad) == 0, (model, bad[:5].tolist(), [len(seqs[i]) for i in bad[0]])
+
+
+def test_host_side_packing_gives_the_same_pool(ctx, monkeypatch):
+    """andi_pool_set_host can pack the pool on the host (host_pack.c: AVX2 / scalar, OpenMP) before
+    the upload (ANDI_B200_HOST_PACK=1) instead of on the device: same GC fractions, separator flags
+    and rows, on inputs with separators, odd lengths and lengths around the 32-base word size."""
+    groups = stress_sequences()
+    seqs = groups["join"] + groups["short"] + [groups["subst"][1][:31], groups["subst"][1][:32], groups["subst"][1][:33],
+                                               groups["subst"][2][:64] + b"!" + groups["subst"][2][64:131]]
+    ctx.set_pool(seqs)
+    device_info = [ctx.pool_info(k) for k in range(len(seqs))]
+    device_rows = ctx.dist_rows(model="JC")
+    monkeypatch.setenv("ANDI_B200_HOST_PACK", "1")
+    ctx.set_pool(seqs)
+    assert [ctx.pool_info(k) for k in range(len(seqs))] == device_info
+    assert np.array_equal(ctx.dist_rows(model="JC"), device_rows)
+    assert np.array_equal(device_rows, oracle.rows(seqs, "JC"))

@@ -1,6 +1,19 @@
 #!/bin/bash
-python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/r2k_gpu_tests.log 2>&1
-tail -15 gpurun_out/r2k_gpu_tests.log | cut -c1-200
-for m in KIMURA LOGDET; do python bench.py --workload c3 --model $m --steps 3 --warmup 3 --no-cpu --no-e2e --no-full --rows 109 2>/dev/null | python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('c3 $m', d['value'], d['ms_per_step'], d['esa_build']['ms_per_subject'], d['roofline']['launch_ms'], d['cub_calls'])"; done
-ANDI_B200_WALK=pipeline python bench.py --workload c3 --model LOGDET --steps 3 --warmup 3 --no-cpu --no-e2e --no-full --rows 109 2>/dev/null | python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('c3 LOGDET pipeline kernel', d['value'], d['ms_per_step'])"
-python bench.py --model LOGDET --steps 2 --warmup 2 --no-cpu --no-e2e --no-full 2>/dev/null | python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('c4 LOGDET', d['value'], d['roofline']['launch_ms'])"
+# final 1-GPU measurement job of round 2 (part 2)
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "host_side or esa_arrays or pathological or many_contigs" > gpurun_out/r2_tests_b.log 2>&1; tail -3 gpurun_out/r2_tests_b.log
+for pc in 1 2; do ANDI_B200_PART_CTAS=$pc python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu --no-e2e --no-full --rows 16 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c5_ctas$pc.json; done
+ANDI_B200_DEPTH_BIAS=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_launches_c4.csv python tools/launch_list.py 64 2100000 3 > /dev/null 2>&1
+python bench.py --steps 4 --warmup 3 2> gpurun_out/r2_bench_n1.err | grep '^{' > gpurun_out/r2_bench_n1.json
+python bench.py --impl reference --steps 2 --warmup 1 2> gpurun_out/r2_bench_ref.err | grep '^{' > gpurun_out/r2_bench_reference_arm.json
+python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu --no-e2e --no-full --rows 29 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c2.json
+python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu --no-e2e --no-full --rows 109 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c3_kimura.json
+python bench.py --workload c3 --model LOGDET --steps 3 --warmup 3 --no-cpu --no-e2e --no-full --rows 109 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c3_logdet.json
+python - <<'PY'
+import json
+for f in ("r2_bench_n1", "r2_bench_reference_arm", "r2_bench_c2", "r2_bench_c3_kimura", "r2_bench_c3_logdet", "r2_bench_c5_ctas1", "r2_bench_c5_ctas2"):
+    try:
+        d = json.load(open(f"gpurun_out/{f}.json"))
+        print(f, round(d["value"]), round(d["ms_per_step"], 2), d.get("e2e") and round(d["e2e"]["value"]), d.get("roofline") and d["roofline"]["launch_ms"], d.get("esa_build") and d["esa_build"]["ms_per_subject"], d.get("parity"), d.get("full_matrix") and d["full_matrix"]["seconds"])
+    except Exception as e:
+        print(f, "ERR", e)
+PY
