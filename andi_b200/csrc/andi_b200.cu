@@ -12,6 +12,8 @@
 #include <cub/device/device_scan.cuh>	// doubling fallback (repeat-rich texts) only
 #include <cub/device/device_select.cuh>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in Nsight Systems (tracing)
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -22,6 +24,12 @@
 #include <vector>
 
 // ------------------------------------------------------------------ plumbing
+
+// NVTX range for the lifetime of a scope: pool upload / index build / walk of one subject
+struct NvtxRange {
+	explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+};
 
 struct andi_ctx {
 	int device = 0;
@@ -467,6 +475,7 @@ static int pool_set_host_packed(andi_ctx *ctx, const char *const *seqs, const si
 
 extern "C" int andi_pool_set_host(andi_ctx *ctx, const char *const *seqs, const size_t *lens, size_t n) {
 	if (!ctx || !seqs) return ANDI_ERR_ARG;
+	NvtxRange range("andi: pool upload + pack");
 	int rc = pool_check(ctx, lens, n);
 	if (rc) return rc;
 	CK(cudaSetDevice(ctx->device));

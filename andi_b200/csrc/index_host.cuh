@@ -354,7 +354,8 @@ rebuild:
 		CK(cudaMemsetAsync(b.pl_idx[0], 0xff, b.pl_cap * sizeof(u32), st));
 	}
 	const bool atomic_path = kmers <= ANDI_BUCKET_ATOMIC_KMERS;
-	bool slots = atomic_path && !sep;  // k_bucket_sort_slots: no bucket tables, one thread per suffix-array slot
+	bool slots = atomic_path && !sep;  // k_bucket_sort_slots: one thread per suffix-array slot
+	bool sorted = false;			   // the bucketing pass has sorted the buckets already (k_part_sort)
 	const bool key_sort = getenv("ANDI_B200_KEY_SORT") != nullptr;  // experiments: the one-thread-per-k-mer kernel on the same tables
 	if (atomic_path) {
 		// counting sort with L2-resident tables: histogram, scan, scatter
@@ -399,9 +400,12 @@ rebuild:
 		if (rc) return rc;
 		CK(cudaMemcpyAsync(hist1, start1, parts * sizeof(u32), cudaMemcpyDeviceToDevice, st));	// cursors
 		k_part_scatter<<<ctas, 1024, parts * sizeof(u32), st>>>(rs, K, K2, per_cta, hist1, b.grp);
-		k_part_sort<<<parts, 1024, bins * sizeof(u32) + 128, st>>>(rs, K, K2, start1, b.grp, E->SA, b.hist, E->dir);
+		presence_layout(E);
+		CK(cudaMemsetAsync(E->present.bits + E->present.offset[K - 1], 0, ((((size_t)1 << (2 * (K - 1))) + 31) / 32) * sizeof(u32), st));
+		k_part_sort<<<parts, 1024, bins * sizeof(u32) + 128, st>>>(rs, K, K2, start1, b.grp, E->SA, b.hist, E->dir, b.flags,
+																	 E->present.bits + E->present.offset[K - 1]);
 		bend = b.hist;	// bucket ends; hist - 1 = bucket starts (hist_alloc holds zeros in front)
-		slots = true;
+		slots = true, sorted = true;
 		ctx->st.esa_launches += 3;
 	} else {
 		// deep directory WITH separators (join mode on a genome of hundreds of Mbp): (key, position)
@@ -435,15 +439,17 @@ rebuild:
 	}
 	presence_layout(E);
 	u32 *present_top = E->present.bits + E->present.offset[K - 1];
-	CK(cudaMemsetAsync(present_top, 0, ((((size_t)1 << (2 * (K - 1))) + 31) / 32) * sizeof(u32), st));
+	if (!sorted) CK(cudaMemsetAsync(present_top, 0, ((((size_t)1 << (2 * (K - 1))) + 31) / 32) * sizeof(u32), st));
 	if (sep) {
 		rc = padded_finish(ctx, E, rs);
 		if (rc) return rc;
 		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, atomic_path, present_top);
 		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	} else {
-		if (slots && !key_sort)
-			k_bucket_sort_slots<<<nblocks(N, 128), 128, 0, st>>>(rs, K, E->SA, E->dir, b.flags, present_top);
+		if (sorted)
+			;
+		else if (slots && !key_sort)
+			k_bucket_sort_slots<<<nblocks(N, 128), 128, 0, st>>>(rs, K, b.hist, E->SA, E->dir, b.flags, present_top);
 		else
 			k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, slots ? b.hist - 1 : b.bstart, bend, nullptr, E->SA, E->dir, b.flags, atomic_path || slots, present_top);
 		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
@@ -492,6 +498,7 @@ rebuild:
 
 // RS planes are in place; build everything else.
 static int build_index(andi_ctx *ctx, andi_esa *E, unsigned flags) {
+	NvtxRange range("andi: index build (esa_init)");
 	cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
 	mark(ctx, e0);
 	if (!ctx->first_ev) {

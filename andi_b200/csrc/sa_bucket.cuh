@@ -334,10 +334,10 @@ __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart
 // ---- k_bucket_sort_slots (texts without separators): the same per-bucket work with one thread per
 // suffix-array SLOT instead of one per k-mer. At depth K = log4(N) + 1 three buckets in four are
 // empty, and a thread per k-mer spends most of the kernel reading table entries of empty buckets
-// (18 % of the whole build in round 1). Here thread j looks at the suffix the bucketing pass left
-// in slot j and at its left neighbour: if their k-mers differ, j is the head of a bucket; it finds
-// the end of the bucket the same way and sorts it. No bucket table is read at all; the entries of
-// EMPTY buckets are written by the scan kernel below. Presence bits (level K-1) by atomicOr.
+// (18 % of the whole build in round 1). Here thread j computes the k-mer of the suffix the bucketing
+// pass left in slot j and reads that ONE bucket's bounds (the scatter cursor table = bucket ends):
+// if the bucket starts at j, j is its head and sorts it. The entries of EMPTY buckets are written
+// by the scan kernel below. Presence bits (level K-1) by atomicOr.
 __device__ __forceinline__ u32 padded_key_nosep(const TextView &rs, u32 p, int K) {
 	const u32 run = p <= rs.mid ? rs.mid - p : rs.len - p;	// nucleotides before '#' / the end
 	u64 cw = window32(rs.code, p);
@@ -345,15 +345,14 @@ __device__ __forceinline__ u32 padded_key_nosep(const TextView &rs, u32 p, int K
 	return kmer_key(cw, K);
 }
 
-__global__ void k_bucket_sort_slots(TextView rs, int K, u32 *__restrict__ SA, u64 *__restrict__ dir64,
+__global__ void k_bucket_sort_slots(TextView rs, int K, const u32 *__restrict__ bend, u32 *__restrict__ SA, u64 *__restrict__ dir64,
 									u32 *__restrict__ n_ambiguous, u32 *__restrict__ present_top) {
 	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= rs.len) return;
+	// the bucket of the suffix in this slot: [bend[key - 1], bend[key]) (bend[-1] is a zero in front of the table)
 	const u32 key = padded_key_nosep(rs, SA[j], K);
-	if (j > 0 && padded_key_nosep(rs, SA[j - 1], K) == key) return;	 // not the head of its bucket
-	u32 e = j + 1;
-	while (e < rs.len && padded_key_nosep(rs, SA[e], K) == key) e++;
-	const u32 count = bucket_sort_range<false>(rs, K, key, j, e, false, SA, dir64, n_ambiguous);
+	if (bend[(int)key - 1] != j) return;  // not the head of its bucket
+	const u32 count = bucket_sort_range<false>(rs, K, key, j, bend[key], false, SA, dir64, n_ambiguous);
 	if (count) {
 		const u32 y = key >> 2;	 // its (K-1)-mer
 		atomicOr(present_top + (y >> 5), 1u << (y & 31u));
@@ -479,7 +478,7 @@ __global__ void __launch_bounds__(256) k_scan_buckets(const u32 *hist, u32 n, u3
 //   level 2  one CTA per part: counting sort of its suffixes on the remaining K2 = K - K1 bases with
 //            a 4^K2-counter histogram in shared memory; it knows every bucket of its part, so it
 //            writes the bucket ends, and the directory entries of the empty buckets, as coalesced
-//            streams (k_part_sort) -> SA grouped by k-mer, exactly what the atomics path leaves
+//            streams, and then sorts its buckets in place (k_part_sort) -> SA ordered up to ties
 // Texts without separators only. Traffic: the text twice (L2), 3 x 4N bytes of positions.
 __global__ void __launch_bounds__(1024) k_part_hist(TextView rs, int K, int K2, u32 per_cta, u32 *__restrict__ hist1) {
 	extern __shared__ u32 sh[];
@@ -511,7 +510,8 @@ __global__ void __launch_bounds__(1024) k_part_scatter(TextView rs, int K, int K
 // start1[x] = first slot of part x (x = blockIdx.x), start1[x + 1] its end. bend[key] = end of bucket key.
 __global__ void __launch_bounds__(1024) k_part_sort(TextView rs, int K, int K2, const u32 *__restrict__ start1,
 													 const u32 *__restrict__ tmp, u32 *__restrict__ SA, u32 *__restrict__ bend,
-													 u64 *__restrict__ dir64) {
+													 u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous,
+													 u32 *__restrict__ present_top) {
 	extern __shared__ u32 sh[];	 // 4^K2 counters, then 32 warp sums
 	const u32 bins = 1u << (2 * K2), mask = bins - 1u, part = blockIdx.x;
 	const u32 s = start1[part], e = start1[part + 1];
@@ -547,6 +547,20 @@ __global__ void __launch_bounds__(1024) k_part_sort(TextView rs, int K, int K2, 
 	for (u32 j = s + threadIdx.x; j < e; j += blockDim.x) {
 		const u32 i = tmp[j];
 		SA[atomicAdd(&sh[padded_key_nosep(rs, i, K) & mask], 1u)] = i;
+	}
+	__syncthreads();
+	// the buckets of this part are complete and this CTA knows where each one lies (the cursors now
+	// hold the bucket ENDS): every thread sorts the buckets of its own bins right here -- no
+	// separate pass over all slots that finds the bucket heads again through the text
+	u32 start = b0 ? sh[b0 - 1] : s;
+	for (u32 x = 0; x < per; x++) {
+		const u32 end = sh[b0 + x];
+		if (end > start) {
+			const u32 key = (u32)(key0 + x);
+			if (bucket_sort_range<false>(rs, K, key, start, end, false, SA, dir64, n_ambiguous))
+				atomicOr(present_top + ((key >> 2) >> 5), 1u << ((key >> 2) & 31u));
+		}
+		start = end;
 	}
 }
 

@@ -93,15 +93,18 @@ def broadcast_pool(ctx, dist, device, rank: int, src: int = 0):
     return words * 8 * len(planes)
 
 
-def dynamic_rows(ctx, n: int, out_dev_ptr: int, take, batch: int, p_value: float = 0.025, model: str = "JC"):
+def dynamic_rows(ctx, n: int, out_dev_ptr: int, take, batch: int, p_value: float = 0.025, model: str = "JC", limit: int | None = None):
     """Rows of M by a shared queue: `take(batch)` returns the first subject of the next batch (an
-    atomic fetch-and-add shared by all ranks, e.g. TCPStore.add) ; rows [b, b + batch) go to
-    out_dev_ptr + b * n * 68 (a full n x n matrix on this rank's device). Returns rows computed."""
+    atomic fetch-and-add shared by all ranks, e.g. TCPStore.add); rows [b, b + batch) go to
+    out_dev_ptr + b * n * 68 (a full n x n matrix on this rank's device). `limit`: end of the
+    subjects this queue hands out (default n; a static block passes its own end). Returns the
+    number of rows computed."""
+    end = n if limit is None else limit
     done = 0
     while True:
         b = take(batch)
-        if b >= n:
+        if b >= end:
             return done
-        e = min(n, b + batch)
+        e = min(end, b + batch)
         ctx.dist_rows_device(out_dev_ptr + b * n * 68, b, e, p_value, model)
         done += e - b

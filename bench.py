@@ -259,9 +259,17 @@ def main():
     store = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-        # a second store of our own: its add() is the atomic counter of the dynamic subject queue
-        store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 1,
-                              world, is_master=(rank == 0))
+        # the atomic counter of the dynamic subject queue: add() of the rendezvous store the process
+        # group already has; else a store of our own on the next port; else static row blocks
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            store.add("andi_probe", 1)
+        except Exception:
+            try:
+                store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 1,
+                                      world, is_master=(rank == 0))
+            except Exception:
+                store = None
 
     g, ln, lo, hi, seed, model = workload_of(args)
     chars, offsets, lens, d = make_pool_device(g, ln, lo, hi, seed, device, args.contigs)
@@ -386,16 +394,18 @@ def main():
         batch = max(1, min(16, g // (world * 8)))
         local_next = [0]
 
+        static_rows = driver.shard_subjects(g, world, rank) if (world > 1 and store is None) else None
+
         def take(b):
             if store is not None:
                 return store.add("andi_next_subject", b) - b
-            v = local_next[0]
+            v = local_next[0] + (static_rows[0] if static_rows else 0)
             local_next[0] += b
             return v
 
         barrier()
         e0.record(stream)
-        mine = driver.dynamic_rows(ctx, g, full.data_ptr(), take, batch, 0.025, model)
+        mine = driver.dynamic_rows(ctx, g, full.data_ptr(), take, batch, 0.025, model, limit=static_rows[1] if static_rows else None)
         if world > 1:
             dist.reduce(full, dst=0, op=dist.ReduceOp.SUM)
         e1.record(stream)
@@ -410,6 +420,7 @@ def main():
         if rank == 0:
             digest = hashlib.blake2b(full.cpu().numpy().tobytes(), digest_size=16).hexdigest()
             full_matrix = {"seconds": ms3 * 1e-3, "pairs_per_s": g * (g - 1) / (ms3 * 1e-3), "rows": g, "queue_batch": batch,
+                           "queue": "shared counter (store.add)" if store is not None else ("static row blocks" if world > 1 else "one rank"),
                            "rows_per_rank": [int(c.item()) for c in all_counts],
                            # the same digest at every N = the N-GPU matrix is the 1-GPU matrix
                            "blake2b_of_matrix": digest}
