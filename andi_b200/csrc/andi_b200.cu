@@ -76,6 +76,8 @@ struct andi_ctx {
 	} bs;
 
 	unsigned long long *walk_counter = nullptr;  // unit dispenser of the walk kernels
+	u32 *walk_bad = nullptr;					 // per pair: a chunk boundary did not synchronise (k_walk_reduce_sum)
+	size_t walk_bad_cap = 0;
 
 	// pinned staging planes of andi_pool_set_host (the pool is packed on the host, host_pack.c)
 	u64 *h_code = nullptr, *h_spec = nullptr;
@@ -255,7 +257,7 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	dfree(ctx, ctx->pool_code), dfree(ctx, ctx->pool_spec), dfree(ctx, ctx->stage_chars);
 	dfree(ctx, ctx->bs.hist_alloc), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
 	dfree(ctx, ctx->bs.scan_state);
-	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter);
+	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter), dfree(ctx, ctx->walk_bad);
 	dfree(ctx, ctx->bs.pl_key[0]), dfree(ctx, ctx->bs.pl_key[1]), dfree(ctx, ctx->bs.pl_idx[0]), dfree(ctx, ctx->bs.pl_idx[1]);
 	dfree(ctx, ctx->bs.fvalid);
 	if (ctx->bs.pl_tmp) cudaFreeAsync(ctx->bs.pl_tmp, ctx->stream);

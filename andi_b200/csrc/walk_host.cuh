@@ -10,14 +10,14 @@
 
 typedef void (*chunks_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, u32 *,
 						  unsigned long long *);
-typedef void (*reduce_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, const u32 *, u32 *);
+typedef void (*reduce_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, const u32 *, const u32 *, u32 *);
 
 static void pick_walk(int model, bool spec, chunks_fn &cf, reduce_fn &rf) {
 	bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
-	if (quarter && spec) cf = k_walk_chunks<true, true>, rf = k_walk_reduce<true, true>;
-	if (quarter && !spec) cf = k_walk_chunks<true, false>, rf = k_walk_reduce<true, false>;
-	if (!quarter && spec) cf = k_walk_chunks<false, true>, rf = k_walk_reduce<false, true>;
-	if (!quarter && !spec) cf = k_walk_chunks<false, false>, rf = k_walk_reduce<false, false>;
+	if (quarter && spec) cf = k_walk_chunks<true, true>, rf = k_walk_reduce_finish<true, true>;
+	if (quarter && !spec) cf = k_walk_chunks<true, false>, rf = k_walk_reduce_finish<true, false>;
+	if (!quarter && spec) cf = k_walk_chunks<false, true>, rf = k_walk_reduce_finish<false, true>;
+	if (!quarter && !spec) cf = k_walk_chunks<false, false>, rf = k_walk_reduce_finish<false, false>;
 }
 
 // Chunk length: aim at ~5 units per resident thread so the dynamic unit queue balances, keep chunks
@@ -136,8 +136,21 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 		cf<<<grid, ANDI_WALK_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
 														 d_records, ctx->walk_counter);
 	}
-	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold,
-												   d_records, d_out);
+	// the records of every pair: summed by a grid of (slice, pair) CTAs, finished (tail, diagonal cell,
+	// pairs with a boundary that did not synchronise) by one warp per pair
+	if (nq > ctx->walk_bad_cap) {
+		dfree(ctx, ctx->walk_bad);
+		ctx->walk_bad_cap = 0;
+		CK(dalloc(ctx, &ctx->walk_bad, nq));
+		ctx->walk_bad_cap = nq;
+	}
+	CK(cudaMemsetAsync(ctx->walk_bad, 0, (size_t)nq * sizeof(u32), ctx->stream));
+	CK(cudaMemsetAsync(d_out, 0, (size_t)nq * 17 * sizeof(u32), ctx->stream));
+	k_walk_reduce_sum<<<dim3(nq, nblocks(plan.cpq, ANDI_REDUCE_SLICE)), 256, 0, ctx->stream>>>(d_queries, d_query_ids, S.self, plan.chunk,
+																								plan.cpq, d_records, d_out, ctx->walk_bad);
+	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records,
+																ctx->walk_bad, d_out);
+	ctx->st.walk_launches += 1;
 	mark(ctx, e1);
 	ctx->walk_ev.emplace_back(e0, e1);
 	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);

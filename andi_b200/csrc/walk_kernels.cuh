@@ -474,27 +474,25 @@ k_walk_chunks(const SubjectIndex S, const QueryView *__restrict__ queries, const
 	}
 }
 
-// ---- k_walk_reduce: one WARP per pair, see the header of this file. Lanes sum the records
-// of 32 consecutive chunks at a time; the first boundary that did not synchronise (if any) is
-// located with a ballot and lane 0 carries the true chain on sequentially from there.
+// ---- the reduction of the unit records of one pair, see the header of this file.
+//
+// reduce_pair_sequential: one WARP per pair. Lanes sum the records of 32 consecutive chunks at a
+// time; the first boundary that did not synchronise (if any) is located with a ballot and lane 0
+// carries the true chain on sequentially from there. Exact for every input; used directly by the
+// round-1 path and as the fallback of the parallel form below.
+//
+// (r2) k_walk_reduce_sum + k_walk_reduce_finish: with all boundaries synchronised (the rule) the
+// result is a plain sum over the records plus the tail, and one warp per pair is far too little
+// parallelism for few, long queries (config 2: 28 warps on the whole GPU, 244 us per subject, a
+// quarter of the walk; config 5: 2 warps, 5.3 ms). Now a grid of (pair, slice of chunks) CTAs sums
+// the records -- lane x of a warp accumulates word x of every record: coalesced -- and adds them
+// to the pair's cell with atomics, noting whether any boundary failed; the finish kernel adds the
+// tail (src/process.c:199-211) or, for a pair with a failed boundary, redoes it sequentially.
 template <bool QUARTER, bool SPEC>
-__global__ void __launch_bounds__(128)
-k_walk_reduce(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
-			  u32 nq, u32 chunk, u32 cpq, u32 threshold, const u32 *__restrict__ records, u32 *__restrict__ out) {
+__device__ void reduce_pair_sequential(const SubjectIndex &S, const TextView &q, u32 t, u32 chunk, const u32 *base, u32 *cell) {
 	const u32 lane = threadIdx.x & 31u;
-	const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (k >= nq) return;  // whole warp
-	u32 qid = query_ids ? query_ids[k] : k;
-	u32 *cell = out + (size_t)k * 17;
-	if (qid == S.self) {
-		// src/dist_hack.h:61-64
-		if (lane < 17) cell[lane] = (lane == 0 || lane == 16) ? 9u : 0u;
-		return;
-	}
-	const TextView q = queries[qid].t;
-	const u32 t = threshold, qlen = q.len;
+	const u32 qlen = q.len;
 	const u32 nch = (u32)(((unsigned long long)qlen + chunk - 1) / chunk);
-	const u32 *base = records + (unsigned long long)k * cpq * ANDI_UNIT_WORDS;
 	LocalAcc total;	 // per lane partial sums
 #pragma unroll
 	for (int x = 0; x < 16; x++) total.c[x] = 0;
@@ -570,6 +568,99 @@ k_walk_reduce(const SubjectIndex S, const QueryView *__restrict__ queries, const
 		if (lane == 0) cell[x] = v;
 	}
 	if (lane == 0) cell[16] = qlen;
+}
+
+template <bool QUARTER, bool SPEC>
+__global__ void __launch_bounds__(128)
+k_walk_reduce(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids,
+			  u32 nq, u32 chunk, u32 cpq, u32 threshold, const u32 *__restrict__ records, u32 *__restrict__ out) {
+	const u32 lane = threadIdx.x & 31u;
+	const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (k >= nq) return;  // whole warp
+	u32 qid = query_ids ? query_ids[k] : k;
+	u32 *cell = out + (size_t)k * 17;
+	if (qid == S.self) {
+		// src/dist_hack.h:61-64
+		if (lane < 17) cell[lane] = (lane == 0 || lane == 16) ? 9u : 0u;
+		return;
+	}
+	reduce_pair_sequential<QUARTER, SPEC>(S, queries[qid].t, threshold, chunk, records + (unsigned long long)k * cpq * ANDI_UNIT_WORDS, cell);
+}
+
+#define ANDI_REDUCE_SLICE 2048u	 // chunks per CTA of k_walk_reduce_sum
+
+// out (nq cells, zeroed by the caller) += sum over the records of the slice; bad[k] = 1 if a boundary
+// of pair k did not synchronise. Grid: (nq, slices); 256 threads = 8 warps, one record per warp and turn.
+__global__ void __launch_bounds__(256)
+k_walk_reduce_sum(const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 self, u32 chunk, u32 cpq,
+				  const u32 *__restrict__ records, u32 *__restrict__ out, u32 *__restrict__ bad) {
+	const u32 k = blockIdx.x, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;	 // grid: (pair, slice)
+	const u32 qid = query_ids ? query_ids[k] : k;
+	if (qid == self) return;
+	const u32 qlen = queries[qid].t.len;
+	const u32 nch = (u32)(((unsigned long long)qlen + chunk - 1) / chunk);
+	const u32 c0 = blockIdx.y * ANDI_REDUCE_SLICE, c1 = min(nch, c0 + ANDI_REDUCE_SLICE);
+	if (c0 >= nch) return;
+	const u32 *base = records + (unsigned long long)k * cpq * ANDI_UNIT_WORDS;
+	u32 sum = 0, any_bad = 0;
+	for (u32 c = c0 + wid; c < c1; c += 8u) {
+		const u32 *rec = base + (unsigned long long)c * ANDI_UNIT_WORDS;
+		sum += rec[lane];									// lanes 0..15: U_c, lanes 16..31: D_c
+		if (lane == 5u) any_bad |= rec[37] == 0u ? 1u : 0u;	// the flag of the boundary behind chunk c
+	}
+	sum += __shfl_down_sync(0xffffffffu, sum, 16);	// lane x < 16: U[x] + D[x]
+	__shared__ u32 part[8][16];
+	__shared__ u32 s_bad;
+	if (threadIdx.x == 0) s_bad = 0;
+	__syncthreads();
+	if (lane < 16u) part[wid][lane] = sum;
+	if (any_bad) s_bad = 1;
+	__syncthreads();
+	if (threadIdx.x < 16u) {
+		u32 v = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) v += part[w][threadIdx.x];
+		if (v) atomicAdd(out + (size_t)k * 17 + threadIdx.x, v);
+	}
+	if (threadIdx.x == 0 && s_bad) bad[k] = 1;
+}
+
+// One warp per pair: the diagonal cell, the tail of a pair whose boundaries all synchronised, or the
+// whole pair again, sequentially, where one did not.
+template <bool QUARTER, bool SPEC>
+__global__ void __launch_bounds__(128)
+k_walk_reduce_finish(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 nq,
+					 u32 chunk, u32 cpq, u32 threshold, const u32 *__restrict__ records, const u32 *__restrict__ bad,
+					 u32 *__restrict__ out) {
+	const u32 lane = threadIdx.x & 31u;
+	const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (k >= nq) return;  // whole warp
+	const u32 qid = query_ids ? query_ids[k] : k;
+	u32 *cell = out + (size_t)k * 17;
+	if (qid == S.self) {
+		// src/dist_hack.h:61-64
+		if (lane < 17) cell[lane] = (lane == 0 || lane == 16) ? 9u : 0u;
+		return;
+	}
+	const TextView q = queries[qid].t;
+	const u32 *base = records + (unsigned long long)k * cpq * ANDI_UNIT_WORDS;
+	if (bad[k]) {
+		reduce_pair_sequential<QUARTER, SPEC>(S, q, threshold, chunk, base, cell);
+		return;
+	}
+	if (lane == 0) {
+		const u32 nch = (u32)(((unsigned long long)q.len + chunk - 1) / chunk);
+		const u32 *rl = base + (unsigned long long)(nch - 1) * ANDI_UNIT_WORDS;
+		WalkState fin;
+		fin.pos_q = rl[32], fin.last_s = rl[33], fin.last_q = rl[34], fin.last_len = rl[35], fin.paired = rl[36];
+		LocalAcc tail;
+#pragma unroll
+		for (int x = 0; x < 16; x++) tail.c[x] = 0;
+		walk_tail<QUARTER, SPEC>(q, threshold, fin, tail);
+#pragma unroll
+		for (int x = 0; x < 16; x++) cell[x] += tail.c[x];
+		cell[16] = q.len;
+	}
 }
 
 // get_match for a batch of packed queries (tests / andi_esa_get_match): the lookup of the walk
