@@ -175,3 +175,38 @@ def test_bootstrap_cell_marginals(host):
         cov = np.cov(draws[:, 0], draws[:, 5])[0, 1]
         want = -N * (counts[0] / N) * (counts[5] / N)
         assert abs(cov - want) < 6 * np.sqrt(counts[0] * counts[5]) / np.sqrt(reps) + 1.0
+
+
+def test_host_packer_layout_and_counts():
+    """host_pack.c (the opt-in host-side 2-bit packing of andi_pool_set_host): code / spec words in the
+    layout of text.cuh (base d of a word at bits 2d, A0 C1 G2 T3 = nucl2bit of src/model.c:295-299,
+    anything else a separator with code 0), G+C count (src/sequence.c:196-207), separator count,
+    zero guard words -- against a numpy restatement, at lengths around the 32-base word and the
+    AVX2 block size, with separators at block borders. No GPU involved."""
+    L = C.CDLL(str(ROOT / "andi_b200" / "libandi_b200.so"))
+    L.andi_host_pack.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.andi_host_pack.restype = None
+    rng = np.random.default_rng(11)
+    code_of = np.full(256, 0, np.uint64)
+    for ch, v in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3)):
+        code_of[ch[0]] = v
+    for n in (1, 31, 32, 33, 63, 64, 65, 1000, 4097, 100003):
+        s = bytearray(np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=n)].tobytes())
+        for pos in {0, n - 1, n // 2, 31 % n, 32 % n, 63 % n}:
+            if rng.random() < 0.5:
+                s[pos] = ord("!")
+        s = bytes(s)
+        nw = n // 32 + 4
+        code, spec = np.full(nw, 0xFFFFFFFFFFFFFFFF, np.uint64), np.full(nw, 0xFFFFFFFFFFFFFFFF, np.uint64)
+        gc, sep = C.c_uint64(0), C.c_uint64(0)
+        L.andi_host_pack(s, n, code.ctypes.data, spec.ctypes.data, nw, C.byref(gc), C.byref(sep))
+        b = np.frombuffer(s, np.uint8)
+        nuc = np.isin(b, np.frombuffer(b"ACGT", np.uint8))
+        padded_c, padded_s = np.zeros(nw * 32, np.uint64), np.zeros(nw * 32, np.uint64)
+        padded_c[:n] = np.where(nuc, code_of[b], 0)
+        padded_s[:n] = (~nuc).astype(np.uint64)
+        shifts = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, :]
+        want_c = (padded_c.reshape(nw, 32) << shifts).sum(axis=1, dtype=np.uint64)
+        want_s = (padded_s.reshape(nw, 32) << shifts).sum(axis=1, dtype=np.uint64)
+        assert np.array_equal(code, want_c) and np.array_equal(spec, want_s), n
+        assert gc.value == int((nuc & ((b == ord("C")) | (b == ord("G")))).sum()) and sep.value == int((~nuc).sum()), n
