@@ -1,5 +1,6 @@
-"""The committed bench line (profiles/r1_bench_n1.json, written by bench.py on a B200) carries
-every key of the measurement contract, and its derived numbers are consistent."""
+"""The committed bench lines (profiles/r1_bench_n1.json, profiles/r2_bench_n1.json, written by
+bench.py on a B200) carry every key of the measurement contract, and their derived numbers are
+consistent."""
 import json
 from pathlib import Path
 
@@ -28,3 +29,28 @@ def test_committed_bench_line_has_the_contract_keys():
     pairs = d["config"]["pairs_per_step"]
     assert abs(d["value"] - pairs / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_round2_bench_line():
+    d = json.loads((ROOT / "profiles" / "r2_bench_n1.json").read_text())
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity", "full_matrix"):
+        assert k in d, k
+    assert d["unit"] == "pairs/s" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None
+    # the benched workload equals the reference cell for cell
+    assert d["parity"]["mismatches"] == 0 and d["parity"]["cells"] > 1000 and d["parity"]["against"] == "reference"
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    want = r["pairs_per_launch"] * r["algorithmic_bytes_per_pair"] / (r["launch_ms"] * 1e-3) / 1e9
+    assert abs(r["achieved"] - want) / want < 1e-6
+    pairs = d["config"]["pairs_per_step"]
+    assert abs(d["value"] - pairs / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    f = d["full_matrix"]
+    assert f["rows"] == 3085 and abs(f["pairs_per_s"] - 3085 * 3084 / f["seconds"]) / f["pairs_per_s"] < 1e-6
+    assert d["cub_calls"] == 0 and d["gpu_launches"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # the traffic file belongs to kernel sources by digest
+    t = json.loads((ROOT / "profiles" / "walk_traffic.json").read_text())
+    assert len(t["kernel_sha"]) == 12 and t["dram_bytes_read"] > 0 and t["pairs_per_launch"] == 3084
