@@ -354,9 +354,8 @@ rebuild:
 		CK(cudaMemsetAsync(b.pl_idx[0], 0xff, b.pl_cap * sizeof(u32), st));
 	}
 	const bool atomic_path = kmers <= ANDI_BUCKET_ATOMIC_KMERS;
-	bool slots = atomic_path && !sep;  // k_bucket_sort_slots: one thread per suffix-array slot
+	bool slots = atomic_path && !sep;  // bucket ends are in hist (hist - 1 = bucket starts), not in bstart / bend tables
 	bool sorted = false;			   // the bucketing pass has sorted the buckets already (k_part_sort)
-	const bool key_sort = getenv("ANDI_B200_KEY_SORT") != nullptr;  // experiments: the one-thread-per-k-mer kernel on the same tables
 	if (atomic_path) {
 		// counting sort with L2-resident tables: histogram, scan, scatter
 		CK(cudaMemsetAsync(b.hist, 0, (kmers + 1) * sizeof(u32), st));
@@ -383,8 +382,8 @@ rebuild:
 		const int K2 = K / 2, K1 = K - K2;
 		const u32 parts = 1u << (2 * K1), bins = 1u << (2 * K2);
 		// one CTA per SM: every CTA keeps one open write sector per part, and 148 x 16384 x 32 B has to stay in L2
-		const char *pc = getenv("ANDI_B200_PART_CTAS");	 // experiments
-		const unsigned ctas = (unsigned)ctx->sm_count * (pc && atoi(pc) == 2 ? 2u : 1u);
+		// (two per SM measured the same: 32.2 vs 32.5 ms per 120 Mbp subject)
+		const unsigned ctas = (unsigned)ctx->sm_count;
 		const u32 per_cta = (N + ctas - 1) / ctas;
 		static bool attr_set = false;
 		if (!attr_set) {
@@ -446,12 +445,9 @@ rebuild:
 		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, atomic_path, present_top);
 		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	} else {
-		if (sorted)
-			;
-		else if (slots && !key_sort)
-			k_bucket_sort_slots<<<nblocks(N, 128), 128, 0, st>>>(rs, K, b.hist, E->SA, E->dir, b.flags, present_top);
-		else
-			k_bucket_sort<false><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, slots ? b.hist - 1 : b.bstart, bend, nullptr, E->SA, E->dir, b.flags, atomic_path || slots, present_top);
+		// (texts without separators: the counting-sort path sorts its buckets with one thread per
+		// slot, the two-level path has sorted them inside k_part_sort already)
+		if (!sorted) k_bucket_sort_slots<<<nblocks(N, 128), 128, 0, st>>>(rs, K, b.hist, E->SA, E->dir, b.flags, present_top);
 		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
 	}
 	ctx->st.esa_launches += 2;

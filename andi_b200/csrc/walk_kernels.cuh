@@ -69,20 +69,28 @@ template <bool SPEC>
 __device__ MatchResult search_range(const SubjectIndex &S, const TextView &q, u32 qpos, u32 rem,
 									u32 lo, u32 hi, u32 nlo, u32 nhi) {
 	const u32 lo0 = nlo, hi0 = nhi;
+	// Manber-Myers acceleration: the query shares m_lo characters with the suffix just below the
+	// current range and m_hi with the one just above it (0 while a bound is still the initial one);
+	// every suffix in between shares at least min(m_lo, m_hi) with it, so the compare starts
+	// there. In a bucket of copies of a long repeat (all suffixes agree for kilobases) this turns
+	// log(bucket) full-length compares into one. (r2: a 2.1 Mbp genome with 30 copies of a
+	// 1.5 kbp element walked 2.6x slower than a repeat-free one, all of it here.)
+	u32 m_lo = 0, m_hi = 0;
 	while (lo < hi) {
 		u32 mid = lo + ((hi - lo) >> 1);
 		u32 p = S.SA[mid];
 		u32 lim = min(rem, rs_run<SPEC>(S.rs, p));
-		u32 c = match_len<SPEC>(q, qpos, S.rs, p, lim);
+		u32 k0 = min(min(m_lo, m_hi), lim);
+		u32 c = k0 + match_len<SPEC>(q, qpos + k0, S.rs, p + k0, lim - k0);
 		bool suffix_less;
 		if (c == rem)
 			suffix_less = false;  // the query is a prefix of this suffix
 		else
 			suffix_less = sym3<SPEC>(S.rs, p + c) < sym3<SPEC>(q, qpos + c);  // q.mid is never hit
 		if (suffix_less)
-			lo = mid + 1;
+			lo = mid + 1, m_lo = c;
 		else
-			hi = mid;
+			hi = mid, m_hi = c;
 	}
 	MatchResult r;
 	r.found_pos = true;

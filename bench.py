@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--length", type=int, default=0, help="override the genome length (experiments only)")
     ap.add_argument("--contigs", type=int, default=0,
                     help="join-mode shape: every genome is this many contigs joined by '!' (experiments only)")
+    ap.add_argument("--repeats", type=int, default=0,
+                    help="realistic repeats: this many copies of a 1.5 kbp element and 7 copies of a 5 kbp operon in the base "
+                         "genome (exact repeats beyond the direct sort / LCP caps: prefix doubling + phi LCP; experiments only)")
     ap.add_argument("--rows", type=int, default=0, help="subjects per step and rank (default: one full walk batch)")
     ap.add_argument("--model", default="")
     ap.add_argument("--no-e2e", action="store_true")
@@ -82,7 +85,7 @@ def divergences(g, lo, hi, seed):
 
 # ----------------------------------------------------------------------------- synthetic pool
 
-def make_pool_device(g, ln, lo, hi, seed, device, contigs=0):
+def make_pool_device(g, ln, lo, hi, seed, device, contigs=0, repeats=0):
     """Star phylogeny on the device (shape of test/test_fasta.cxx): uniform base genome, genome k
     gets exactly round(len * d_k) substitutions at distinct uniform positions."""
     import torch
@@ -92,6 +95,12 @@ def make_pool_device(g, ln, lo, hi, seed, device, contigs=0):
     stride = (ln + 15) // 16 * 16
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
     base = torch.randint(0, 4, (ln,), dtype=torch.uint8, device=device, generator=gen)
+    if repeats:  # IS-element-like and rRNA-operon-like exact repeats (bacterial genomes carry both)
+        element, operon = base[:1500].clone(), base[2000:7000].clone()
+        for at in torch.randint(10000, ln - 10000, (repeats,), device=device, generator=gen).tolist():
+            base[at : at + 1500] = element
+        for at in torch.randint(10000, ln - 10000, (7,), device=device, generator=gen).tolist():
+            base[at : at + 5000] = operon
     chars = torch.zeros(g * stride, dtype=torch.uint8, device=device)
     d = divergences(g, lo, hi, seed)
     for k in range(g):
@@ -272,7 +281,7 @@ def main():
                 store = None
 
     g, ln, lo, hi, seed, model = workload_of(args)
-    chars, offsets, lens, d = make_pool_device(g, ln, lo, hi, seed, device, args.contigs)
+    chars, offsets, lens, d = make_pool_device(g, ln, lo, hi, seed, device, args.contigs, args.repeats)
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
@@ -440,7 +449,7 @@ def main():
     achieved = pairs_per_launch * bytes_per_pair / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0
     traffic, traffic_src = None, None
     tf = ROOT / "profiles" / "walk_traffic.json"
-    if tf.exists() and args.workload == "c4" and not args.genomes and not args.length and not args.contigs:
+    if tf.exists() and args.workload == "c4" and not args.genomes and not args.length and not args.contigs and not args.repeats:
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (tools/capture_traffic.sh);
         # only a capture of THIS build of the kernels counts
         t_ = json.loads(tf.read_text())

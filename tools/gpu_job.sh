@@ -1,10 +1,18 @@
 #!/bin/bash
-# scaling: the bench the way the driver launches it, N ranks on one box
-N=${1:-8}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 4 --warmup 3 2> gpurun_out/r2_bench_n$N.err | grep '^{' > gpurun_out/r2_bench_n$N.json
-tail -3 gpurun_out/r2_bench_n$N.err | cut -c1-300
-python - $N <<'PY'
-import json, sys
-d = json.load(open(f"gpurun_out/r2_bench_n{sys.argv[1]}.json"))
-print("N", d["n_gpus"], "value", round(d["value"]), "ms/step", round(d["ms_per_step"], 1), "e2e", d["e2e"], "full", d["full_matrix"], "clocks", d["clocks"])
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_walk|k_lcp|k_plcp|k_phi|k_round|k_apply|k_head|k_bucket" -c 60 --csv --log-file gpurun_out/r2_launches_repeats.csv python bench.py --genomes 512 --repeats 30 --steps 1 --warmup 0 --rows 2 --no-cpu --no-e2e --no-full > /dev/null 2>&1
+python - <<'PY'
+import csv, collections
+rows=[r for r in csv.reader(open("gpurun_out/r2_launches_repeats.csv")) if len(r)>5]
+hdr=[i for i,r in enumerate(rows) if r[0]=='ID'][0]
+h=rows[hdr]; ix={n:i for i,n in enumerate(h)}
+agg=collections.OrderedDict()
+for r in rows[hdr+2:]:
+    try:
+        k=r[ix['Kernel Name']].split('(')[0][:60]; v=float(r[ix['Metric Value']].replace(',',''))
+    except Exception: continue
+    u=r[ix['Metric Unit']]
+    v = v/1000 if u=='ns' else v*1000 if u=='ms' else v
+    a=agg.setdefault(k,[0,0.0]); a[0]+=1; a[1]+=v
+for k,a in sorted(agg.items(), key=lambda x:-x[1][1])[:14]:
+    print(f"  {k:60s} {a[0]:4d} {a[1]:10.1f} per-launch {a[1]/a[0]:8.1f}")
 PY
