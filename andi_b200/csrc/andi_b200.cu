@@ -76,6 +76,7 @@ struct andi_ctx {
 	} bs;
 
 	unsigned long long *walk_counter = nullptr;  // unit dispenser of the walk kernels
+	bool part_attr_set = false;					 // k_part_* may use 64 KB of dynamic shared memory on this device
 	u32 *walk_bad = nullptr;					 // per pair: a chunk boundary did not synchronise (k_walk_reduce_sum)
 	size_t walk_bad_cap = 0;
 

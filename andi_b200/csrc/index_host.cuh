@@ -385,12 +385,11 @@ rebuild:
 		// (two per SM measured the same: 32.2 vs 32.5 ms per 120 Mbp subject)
 		const unsigned ctas = (unsigned)ctx->sm_count;
 		const u32 per_cta = (N + ctas - 1) / ctas;
-		static bool attr_set = false;
-		if (!attr_set) {
+		if (!ctx->part_attr_set) {	// per device: a function attribute belongs to the device's context
 			CK(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
 			CK(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
 			CK(cudaFuncSetAttribute(k_part_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 128));
-			attr_set = true;
+			ctx->part_attr_set = true;
 		}
 		u32 *hist1 = b.bstart, *start1 = b.bstart + parts + 4;	 // level-1 tables live in the (unused) bucket-start scratch
 		CK(cudaMemsetAsync(hist1, 0, (parts + 1) * sizeof(u32), st));

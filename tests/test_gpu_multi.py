@@ -76,3 +76,17 @@ def test_cli_on_two_devices_prints_the_same_matrix(tmp_path):
     assert two.returncode == one.returncode == ref.returncode == 0, two.stderr.decode()
     assert two.stdout == one.stdout == ref.stdout
     assert b"Comparing 7 sequences: 100.0% (42/42), done." in two.stderr
+
+
+@needs_two
+def test_deep_directory_on_every_device():
+    """20 Mbp genomes (directory depth 13: the two-level counting sort with 64 KB of dynamic shared
+    memory, an attribute that has to be set per device): the matrix from two devices equals the
+    one-GPU matrix (which test_large_genomes_against_reference pins to the reference)."""
+    seqs = synth.star_phylogeny(3, 20_000_000, [0.0, 0.03, 0.01], seed=4242)
+    ctx = native.Context(0)
+    ctx.set_pool(seqs)
+    single = ctx.dist_rows()
+    ctx.close()
+    assert np.array_equal(native.dist_matrix_multi([0, 1], seqs), single)
+    assert np.array_equal(native.dist_matrix_multi([1], seqs), single)
