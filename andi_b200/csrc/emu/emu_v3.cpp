@@ -23,7 +23,7 @@ typedef uint32_t u32;
 #define V3_SERVE_EVERY 8u
 #define V3_COUNT_STATS 1
 
-enum { ST_trips, ST_ext_trips, ST_cand_trips, ST_steps, ST_lucky_hits, ST_lookups, ST_tag0, ST_tag1, ST_wide_gaps, ST_slow_steps, ST_slow_tail, ST_slow_tag3, ST_wide_pairs, ST_slow_long, ST_cols_trips, ST_pushes, ST_drained, ST_drains, ST_drain_rounds,
+enum { ST_trips, ST_ext_trips, ST_cand_trips, ST_steps, ST_lucky_hits, ST_lookups, ST_tag0, ST_tag1, ST_wide_gaps, ST_slow_steps, ST_slow_tail, ST_slow_tag3, ST_wide_pairs, ST_slow_long, ST_cols_trips, ST_pushes, ST_drained, ST_drains, ST_drain_rounds, ST_coop_scans,
 	   ST_warp_trips, ST_running_lanes, ST_services, ST_served_lanes, ST_N };
 static u64 *g_stats = nullptr;
 #define V3_STAT(name)                \

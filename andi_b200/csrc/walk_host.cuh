@@ -151,6 +151,26 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records,
 																ctx->walk_bad, d_out);
 	ctx->st.walk_launches += 1;
+	static const bool debug_bad = getenv("ANDI_B200_DEBUG_BAD") != nullptr;  // experiments: which boundaries did not synchronise
+	if (debug_bad) {
+		std::vector<u32> bad(nq);
+		CK(cudaMemcpyAsync(bad.data(), ctx->walk_bad, (size_t)nq * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		u32 nbad = 0, first = nq;
+		for (u32 k = 0; k < nq; k++)
+			if (bad[k]) nbad++, first = first == nq ? k : first;
+		fprintf(stderr, "[andi_b200] subject %u: %u of %u pairs with a boundary that did not synchronise\n", S.self, nbad, nq);
+		if (first < nq) {
+			std::vector<u32> rec((size_t)plan.cpq * ANDI_UNIT_WORDS);
+			CK(cudaMemcpy(rec.data(), d_records + (size_t)first * plan.cpq * ANDI_UNIT_WORDS, rec.size() * sizeof(u32), cudaMemcpyDeviceToHost));
+			for (u32 ch = 0; ch + 1 < plan.cpq; ch++) {
+				const u32 *r = &rec[(size_t)ch * ANDI_UNIT_WORDS], *n = r + ANDI_UNIT_WORDS;
+				if (!r[37])
+					fprintf(stderr, "  pair %u boundary after chunk %u (at %llu): E = pos %u, last (s %u, q %u, len %u), paired %u; next chunk's E = pos %u, last (s %u, q %u, len %u)\n",
+							first, ch, (unsigned long long)(ch + 1) * plan.chunk, r[32], r[33], r[34], r[35], r[36], n[32], n[33], n[34], n[35]);
+			}
+		}
+	}
 	mark(ctx, e1);
 	ctx->walk_ev.emplace_back(e0, e1);
 	if (!ctx->last_ev) ctx->last_ev = get_event(ctx);

@@ -40,7 +40,53 @@ struct V3Lane;
 struct V3Const;
 V3_FN void v3_count_slice(const V3Lane &L, const V3Const &c, u32 *col, u32 sign);
 
+#define V3_COOP_IN_WARP_LOOP 1  // requests V3_SVC_COOP / V3_SVC_COOP2 are served by v3_coop_scan below, not by v3_service
 #include "walk_v3_lane.h"
+
+// v3_scan_full (walk_v3_lane.h) by the whole warp: the requests of the lanes in `want`, one after the
+// other; every lane takes one candidate of the request (32 per round) and all candidates grow
+// together, one 64-column window per iteration, until the last of them has met its first mismatch
+// or its limit. Called with all 32 lanes.
+V3_FN void v3_coop_scan(V3Lane &L, const V3Const &c, unsigned want) {
+	const u32 lane = threadIdx.x & 31u;
+	while (want) {
+		const int r = __ffs((int)want) - 1;
+		want &= want - 1u;
+		const bool two = __shfl_sync(0xffffffffu, L.svc, r) == V3_SVC_COOP2;
+		const u32 a = __shfl_sync(0xffffffffu, L.cand_p, r), b = __shfl_sync(0xffffffffu, L.cand2, r);
+		const u32 pos = __shfl_sync(0xffffffffu, L.pos, r), qlen = __shfl_sync(0xffffffffu, L.qlen, r);
+		const u64 *q_code = reinterpret_cast<const u64 *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(L.q_code), r));
+		const u32 count = two ? 2u : b, rem = qlen - pos;
+		u32 best = 0, best_p = 0, best_n = 0;
+		for (u32 base = 0; base < count; base += 32u) {
+			const u32 k = base + lane;
+			const bool have = k < count;
+			u32 p = 0;
+			if (have) p = two ? (k ? b : a) : __ldg(c.SA + a + k);
+			const u32 run = p < c.mid ? c.mid - p : (p == c.mid ? 0u : c.N - p);
+			const u32 lim = have ? (rem < run ? rem : run) : 0u;
+			u32 len = 0;
+			bool alive = len < lim;
+			while (__any_sync(0xffffffffu, alive)) {
+				if (alive) {
+					u64 q0, q1, s0, s1;
+					window64(q_code, pos + len, q0, q1);
+					window64(c.s_code, p + len, s0, s1);
+					const u32 D = v3_first_diff(q0 ^ s0, q1 ^ s1);
+					len += D < lim - len ? D : lim - len;
+					alive = D >= 64u && len < lim;
+				}
+			}
+			const u32 top = __reduce_max_sync(0xffffffffu, have ? len : 0u);
+			const unsigned at_top = __ballot_sync(0xffffffffu, have && len == top);
+			const u32 n = (u32)__popc(at_top), p_top = __shfl_sync(0xffffffffu, p, __ffs((int)at_top) - 1);
+			best_n = top > best ? n : (top == best ? best_n + n : best_n);
+			best_p = top > best ? p_top : best_p;
+			best = top > best ? top : best;
+		}
+		if ((int)lane == r) L.cand_p = best_p, L.len1 = best, L.cand2 = best_n == 1u ? 1u : 0u, L.job = V3_RESOLVED, L.svc = V3_RUN;
+	}
+}
 
 // model.c:259-278 in O(1): the composition of the query slice [lq, lq + ll) from the per-word prefix
 // composition of the pool (k_comp_prefix): two table entries and the two partial words at the ends.
@@ -128,6 +174,9 @@ k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32
 		if (v3_serve_now((u32)__popc(parked), (u32)__popc(running), trip)) {
 			if (L.svc != V3_RUN && L.svc != V3_SVC_DONE) v3_service<PHASE, QUARTER>(L, c, env, col, P);
 			__syncwarp();
+			// (after the lane services: a lean bucket scan that met a repeat has just become a request)
+			const unsigned coop = __ballot_sync(0xffffffffu, L.svc == V3_SVC_COOP || L.svc == V3_SVC_COOP2);
+			if (coop) v3_coop_scan(L, c, coop);
 		}
 		if (__any_sync(0xffffffffu, L.npend > V3_PEND_SLOTS - 2u)) {
 			// a queue is nearly full: the whole warp classifies what it has queued

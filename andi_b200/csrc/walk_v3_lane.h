@@ -36,9 +36,12 @@
 #error "define V3_FN and the v3_* primitives before including walk_v3_lane.h"
 #endif
 
-enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V3_SVC_DONE = 4, V3_SVC_SCAN = 5 };
+enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V3_SVC_DONE = 4, V3_SVC_SCAN = 5, V3_SVC_COOP = 6, V3_SVC_COOP2 = 7 };
 enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND1 = 3, V3_CAND2 = 4, V3_RESOLVED = 5 };
+#ifndef V3_SCAN_MAX
 #define V3_SCAN_MAX 8u  // buckets up to this size are scanned by the lean service routine
+#endif
+#define V3_COOP_MAX 4096u  // ... and up to this size, or with matches longer than a window, by the whole warp (v3_scan_full)
 
 #define V3_EVEN 0x5555555555555555ULL
 #define V3_MAX_T 31u	   // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
@@ -223,7 +226,9 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	}
 	u32 next_job = c1 ? (u32)V3_CAND2 : (ext_done ? (u32)V3_STEP : job);
 	if (ext_done) L.pos = L.lq + L.ll + 1u;
-	if (slow_long) next_job = V3_STEP, L.svc = V3_SVC_SLOW;
+	// two suffixes that both run past the window (a repeat with two copies): the whole warp compares
+	// them to their ends (v3_scan_full); both positions are in cand_p / cand2 after the swap above
+	if (slow_long) next_job = V3_STEP, L.svc = V3_SVC_COOP2;
 	L.job = next_job;
 	// what goes to the pending-gap queue at the end of this trip: COLS trips fetch the gap columns of
 	// an anchor that paired over more than V3_MAX_T columns, 32 per trip
@@ -279,7 +284,8 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 			if (tag == 2u) L.cand_p = p1_diag ? p2 : p1, L.cand2 = p1_diag ? p1 : p2, L.job = V3_CAND1;
 			if (tag == 3u) {  // three or more: the service routine scans the bucket
 				V3_STAT(slow_tag3);
-				L.cand_p = (u32)fe, L.cand2 = (u32)(fe >> 32) & 0x3fffffffu, L.svc = V3_SVC_SCAN;
+				L.cand_p = (u32)fe, L.cand2 = (u32)(fe >> 32) & 0x3fffffffu;
+				L.svc = L.cand2 <= V3_SCAN_MAX ? V3_SVC_SCAN : (L.cand2 <= V3_COOP_MAX ? V3_SVC_COOP : V3_SVC_SLOW);
 			}
 		}
 	}
@@ -388,6 +394,39 @@ V3_FN void v3_finish_unit(const V3Lane &L, u32 *rec, const u32 *col) {
 	}
 }
 
+// Requests V3_SVC_COOP (a bucket: L.cand_p = first SA index, L.cand2 = number of suffixes) and
+// V3_SVC_COOP2 (the two suffixes L.cand_p, L.cand2 of a tag-2 entry): every candidate is compared with
+// the query at pos_Q TO THE END of its match, however long; the longest is the match, unique if no
+// other is as long (process.c:117-122). Result as the lean scan leaves it: job RESOLVED, cand_p = a
+// best candidate, len1 = its length, cand2 = unique. Inside repeats (IS elements, rRNA operons) every
+// directory lookup lands here; the generic step (one lane, binary search with kilobase compares) took
+// about 10 us for each, which made a pool with realistic repeats 2.3 times slower than one without.
+// This is the serial form (the emulation, and the specification of the kernel's warp-wide form
+// v3_coop_scan in walk_v3.cuh: one candidate per lane, all growing together).
+V3_FN void v3_scan_full(V3Lane &L, const V3Const &c) {
+	const bool two = L.svc == V3_SVC_COOP2;
+	const u32 a = L.cand_p, b = L.cand2, count = two ? 2u : b, rem = L.qlen - L.pos;
+	u32 best = 0, best_p = 0, best_n = 0;
+	for (u32 k = 0; k < count; k++) {
+		const u32 p = two ? (k ? b : a) : v3_ld_sa(c.SA + a + k);
+		const u32 run = p < c.mid ? c.mid - p : (p == c.mid ? 0u : c.N - p), lim = rem < run ? rem : run;
+		u32 len = 0;
+		while (len < lim) {
+			u64 q0, q1, s0, s1;
+			v3_window64(L.q_code, L.pos + len, q0, q1);
+			v3_window64(c.s_code, p + len, s0, s1);
+			const u32 D = v3_first_diff(q0 ^ s0, q1 ^ s1);
+			len += D < lim - len ? D : lim - len;
+			if (D < 64u) break;
+		}
+		best_n = len > best ? 1u : (len == best ? best_n + 1u : best_n);
+		best_p = len > best ? p : best_p;
+		best = len > best ? len : best;
+	}
+	V3_STAT(coop_scans);
+	L.cand_p = best_p, L.len1 = best, L.cand2 = best_n == 1u ? 1u : 0u, L.job = V3_RESOLVED, L.svc = V3_RUN;
+}
+
 // Serve one parked lane. Env supplies what differs between the kernel and the emulation:
 //   u64 total; u32 *records; u64 next_unit(); bool open_unit(u64 unit, V3Lane &, u32 *&rec)  (query lookup +
 //   v3_begin_unit; false = no work in this unit); void slow_step(V3Lane &, u32 *col, u32 sign).
@@ -419,8 +458,17 @@ V3_FN void v3_service(V3Lane &L, const V3Const &c, Env &env, u32 *col, const V3P
 			L.cand_p = best_p, L.len1 = best, L.cand2 = best_n == 1u ? 1u : 0u, L.job = V3_RESOLVED, L.svc = V3_RUN;
 			return;
 		}
-		L.svc = V3_SVC_SLOW;
+		L.svc = V3_SVC_COOP;  // a candidate runs past the window (a repeat): compared to its end by the whole warp
+#ifdef V3_COOP_IN_WARP_LOOP
+		return;	 // ... at the next service stop (the kernel's warp loop serves these requests itself)
+#endif
 	}
+#ifndef V3_COOP_IN_WARP_LOOP
+	if (L.svc == V3_SVC_COOP || L.svc == V3_SVC_COOP2) {
+		v3_scan_full(L, c);
+		return;
+	}
+#endif
 	if (L.svc == V3_SVC_SLOW) {
 		env.template slow_step<QUARTER>(L, col, (PHASE == 2 && !L.a_true) ? 0xffffffffu : 1u);
 		L.svc = V3_RUN;

@@ -43,6 +43,16 @@ def stress_sequences():
     rep = base[0][:5000] * 3 + base[0][5000:12000] + base[0][2000:4000] + base[0][12000:]
     out["repeat"] = [rep, synth.star_phylogeny(2, len(rep), [0.0, 0.02], seed=3)[1], base[1]]
     out["identical"] = [base[0], base[0], base[1]]
+    # realistic repeats: one element in 12 copies (directory buckets beyond the lean scan) and one 3 kbp
+    # segment in two copies (tag-2 entries whose candidates both run past a window); the genomes are
+    # mutated independently afterwards, so the copies of a subject differ from the query's
+    import numpy as np
+
+    g = synth.base_genome(40000, seed=21)
+    for i in range(12):
+        g[3000 + 2900 * i : 3700 + 2900 * i] = g[1000:1700]
+    g[36500:39500] = g[500:3500]
+    out["copies"] = [synth.ACGT[synth.mutate(g, p, seed=40 + k)].tobytes() for k, p in enumerate((0.0, 0.01, 0.03))]
     unrelated = synth.star_phylogeny(1, 20000, [0.0], seed=99)[0]
     out["unrelated"] = [base[0], unrelated]
     out["short"] = [base[0][:50], base[1][:50], base[0][:300], base[1][10:400]]
