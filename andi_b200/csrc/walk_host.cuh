@@ -10,7 +10,7 @@
 
 typedef void (*chunks_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, u32 *,
 						  unsigned long long *);
-typedef void (*reduce_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, const u32 *, const u32 *, u32 *);
+typedef void (*reduce_fn)(const SubjectIndex, const QueryView *, const u32 *, u32, u32, u32, u32, const u32 *, const u32 *, u32 *, u32);
 
 static void pick_walk(int model, bool spec, chunks_fn &cf, reduce_fn &rf) {
 	bool quarter = model == ANDI_M_RAW || model == ANDI_M_JC || model == ANDI_M_KIMURA;
@@ -149,7 +149,7 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	k_walk_reduce_sum<<<dim3(nq, nblocks(plan.cpq, ANDI_REDUCE_SLICE)), 256, 0, ctx->stream>>>(d_queries, d_query_ids, S.self, plan.chunk,
 																								plan.cpq, d_records, d_out, ctx->walk_bad);
 	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records,
-																ctx->walk_bad, d_out);
+																ctx->walk_bad, d_out, v3 ? 1u : 0u);
 	ctx->st.walk_launches += 1;
 	static const bool debug_bad = getenv("ANDI_B200_DEBUG_BAD") != nullptr;  // experiments: which boundaries did not synchronise
 	if (debug_bad) {

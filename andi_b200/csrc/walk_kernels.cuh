@@ -597,8 +597,8 @@ k_walk_reduce(const SubjectIndex S, const QueryView *__restrict__ queries, const
 
 #define ANDI_REDUCE_SLICE 2048u	 // chunks per CTA of k_walk_reduce_sum
 
-// out (nq cells, zeroed by the caller) += sum over the records of the slice; bad[k] = 1 if a boundary
-// of pair k did not synchronise. Grid: (nq, slices); 256 threads = 8 warps, one record per warp and turn.
+// out (nq cells, zeroed by the caller) += sum over the records of the slice; bad[k] (zeroed by the
+// caller) = 0xffffffff - c for the first chunk c of pair k whose boundary did not synchronise. Grid: (nq, slices); 256 threads = 8 warps, one record per warp and turn.
 __global__ void __launch_bounds__(256)
 k_walk_reduce_sum(const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 self, u32 chunk, u32 cpq,
 				  const u32 *__restrict__ records, u32 *__restrict__ out, u32 *__restrict__ bad) {
@@ -610,11 +610,11 @@ k_walk_reduce_sum(const QueryView *__restrict__ queries, const u32 *__restrict__
 	const u32 c0 = blockIdx.y * ANDI_REDUCE_SLICE, c1 = min(nch, c0 + ANDI_REDUCE_SLICE);
 	if (c0 >= nch) return;
 	const u32 *base = records + (unsigned long long)k * cpq * ANDI_UNIT_WORDS;
-	u32 sum = 0, any_bad = 0;
+	u32 sum = 0, first_bad = 0xffffffffu;
 	for (u32 c = c0 + wid; c < c1; c += 8u) {
 		const u32 *rec = base + (unsigned long long)c * ANDI_UNIT_WORDS;
-		sum += rec[lane];									// lanes 0..15: U_c, lanes 16..31: D_c
-		if (lane == 5u) any_bad |= rec[37] == 0u ? 1u : 0u;	// the flag of the boundary behind chunk c
+		sum += rec[lane];												 // lanes 0..15: U_c, lanes 16..31: D_c
+		if (lane == 5u && rec[37] == 0u) first_bad = min(first_bad, c);	 // the flag of the boundary behind chunk c
 	}
 	sum += __shfl_down_sync(0xffffffffu, sum, 16);	// lane x < 16: U[x] + D[x]
 	__shared__ u32 part[8][16];
@@ -622,7 +622,7 @@ k_walk_reduce_sum(const QueryView *__restrict__ queries, const u32 *__restrict__
 	if (threadIdx.x == 0) s_bad = 0;
 	__syncthreads();
 	if (lane < 16u) part[wid][lane] = sum;
-	if (any_bad) s_bad = 1;
+	if (first_bad != 0xffffffffu) atomicMax(&s_bad, 0xffffffffu - first_bad);
 	__syncthreads();
 	if (threadIdx.x < 16u) {
 		u32 v = 0;
@@ -630,7 +630,7 @@ k_walk_reduce_sum(const QueryView *__restrict__ queries, const u32 *__restrict__
 		for (int w = 0; w < 8; w++) v += part[w][threadIdx.x];
 		if (v) atomicAdd(out + (size_t)k * 17 + threadIdx.x, v);
 	}
-	if (threadIdx.x == 0 && s_bad) bad[k] = 1;
+	if (threadIdx.x == 0 && s_bad) atomicMax(bad + k, s_bad);
 }
 
 // One warp per pair: the diagonal cell, the tail of a pair whose boundaries all synchronised, or the
@@ -639,7 +639,7 @@ template <bool QUARTER, bool SPEC>
 __global__ void __launch_bounds__(128)
 k_walk_reduce_finish(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 nq,
 					 u32 chunk, u32 cpq, u32 threshold, const u32 *__restrict__ records, const u32 *__restrict__ bad,
-					 u32 *__restrict__ out) {
+					 u32 *__restrict__ out, u32 extended) {
 	const u32 lane = threadIdx.x & 31u;
 	const u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (k >= nq) return;  // whole warp
@@ -652,13 +652,17 @@ k_walk_reduce_finish(const SubjectIndex S, const QueryView *__restrict__ queries
 	}
 	const TextView q = queries[qid].t;
 	const u32 *base = records + (unsigned long long)k * cpq * ANDI_UNIT_WORDS;
-	if (bad[k]) {
+	// extended (records of k_walk_v3): every boundary's correction is valid wherever its chains met, the
+	// sum is complete; chains that reached the end of the query apart left the true final state in the
+	// record of the first such chunk. Else (k_walk_chunks, k_walk_chunks_fast: the replay stops at the end
+	// of the next chunk): the pair is redone sequentially from its first unsynchronised boundary.
+	if (bad[k] && !extended) {
 		reduce_pair_sequential<QUARTER, SPEC>(S, q, threshold, chunk, base, cell);
 		return;
 	}
 	if (lane == 0) {
 		const u32 nch = (u32)(((unsigned long long)q.len + chunk - 1) / chunk);
-		const u32 *rl = base + (unsigned long long)(nch - 1) * ANDI_UNIT_WORDS;
+		const u32 *rl = base + (unsigned long long)(bad[k] ? 0xffffffffu - bad[k] : nch - 1) * ANDI_UNIT_WORDS;
 		WalkState fin;
 		fin.pos_q = rl[32], fin.last_s = rl[33], fin.last_q = rl[34], fin.last_len = rl[35], fin.paired = rl[36];
 		LocalAcc tail;

@@ -36,12 +36,9 @@
 #error "define V3_FN and the v3_* primitives before including walk_v3_lane.h"
 #endif
 
-enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V3_SVC_DONE = 4, V3_SVC_SCAN = 5, V3_SVC_COOP = 6, V3_SVC_COOP2 = 7 };
+enum : u32 { V3_RUN = 0, V3_SVC_FETCH = 1, V3_SVC_FINISH = 2, V3_SVC_SLOW = 3, V3_SVC_DONE = 4, V3_SVC_COOP = 5, V3_SVC_COOP2 = 6 };
 enum : u32 { V3_STEP = 0, V3_EXT = 1, V3_COLS = 2, V3_CAND1 = 3, V3_CAND2 = 4, V3_RESOLVED = 5 };
-#ifndef V3_SCAN_MAX
-#define V3_SCAN_MAX 8u  // buckets up to this size are scanned by the lean service routine
-#endif
-#define V3_COOP_MAX 4096u  // ... and up to this size, or with matches longer than a window, by the whole warp (v3_scan_full)
+#define V3_COOP_MAX 4096u  // buckets up to this size are scanned by the whole warp (v3_scan_full), larger ones by the generic step
 
 #define V3_EVEN 0x5555555555555555ULL
 #define V3_MAX_T 31u	   // the gap columns of a lucky anchor (<= threshold of them) lie in the low window word
@@ -140,11 +137,16 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 				return;
 			}
 		} else {
-			// the two chains inside chunk c+1 (L.c_end = its end): stop when they are in the same
-			// state, give up when either leaves the chunk, else advance the one that is behind
+			// the two chains from the start of chunk c+1 on (L.c_end = the end of the QUERY): stop when
+			// they are in the same state, else advance the one that is behind -- for as long as it takes,
+			// beyond chunk c+1 if need be (a boundary inside a repeat, an anchor-free stretch). The
+			// correction stays exact wherever they meet: with X_j = the amnesic chain of chunk j carried on
+			// to the end of the query and W_j its counts from the start of chunk j, W_j = U_j + D_j +
+			// W_(j+1) holds for D_j = (X_j minus X_(j+1) up to their meeting point), whichever chunk that
+			// point lies in. Chains that reach the end of the query apart (flag 0) have D_j just the same.
 			bool same = L.pos == L.b_pos && L.ls == L.b_ls && L.lq == L.b_lq && L.ll == L.b_ll && L.paired == L.b_paired;
 			u32 t_pos = L.a_true ? L.pos : L.b_pos, p_pos = L.a_true ? L.b_pos : L.pos;
-			if (same || t_pos >= L.c_end || p_pos >= L.c_end) {
+			if (same || (t_pos >= L.c_end && p_pos >= L.c_end)) {
 				L.flag = same ? 1u : 0u;
 				L.svc = V3_SVC_FINISH;
 				return;
@@ -208,7 +210,7 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	// CAND1 (first of two suffixes that carry the k-mer): remember its length, compare the other one.
 	// CAND2: the longer of the two is the match; equal lengths = not unique (process.c:122).
 	// A candidate longer than the window is fine when it is the only / the longer one (EXT follows).
-	// RESOLVED: the service routine has scanned a bucket of three or more (v3_service): best
+	// RESOLVED: the bucket scan is done (v3_scan_full: three or more suffixes, or two long ones): best
 	// candidate in cand_p, its length in len1, cand2 = unique; this trip only accounts for it.
 	const bool slow_long = (c1 && !complete) || (c2 && !complete && l1 >= matched);
 	const bool tie = (c2 && l1 == matched) || (c3 && L.cand2 == 0u), first_better = c2 && l1 > matched;
@@ -285,7 +287,7 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 			if (tag == 3u) {  // three or more: the service routine scans the bucket
 				V3_STAT(slow_tag3);
 				L.cand_p = (u32)fe, L.cand2 = (u32)(fe >> 32) & 0x3fffffffu;
-				L.svc = L.cand2 <= V3_SCAN_MAX ? V3_SVC_SCAN : (L.cand2 <= V3_COOP_MAX ? V3_SVC_COOP : V3_SVC_SLOW);
+				L.svc = L.cand2 <= V3_COOP_MAX ? V3_SVC_COOP : V3_SVC_SLOW;
 			}
 		}
 	}
@@ -349,7 +351,7 @@ template <int PHASE>
 V3_FN bool v3_begin_unit(V3Lane &L, const V3Const &c, const u64 *q_code, u32 qlen, u32 chunk_no, u32 *rec, u32 *col) {
 	const u64 start = (u64)chunk_no * c.chunk;
 	if (start >= qlen) return false;
-	const u64 end1 = start + c.chunk, end2 = start + 2ULL * c.chunk;
+	const u64 end1 = start + c.chunk;
 	const u32 c_end = (u32)(end1 < qlen ? end1 : qlen);
 	if (PHASE == 2 && c_end >= qlen) return false;	// last chunk: no boundary
 	L.q_code = q_code, L.qlen = qlen;
@@ -370,7 +372,7 @@ V3_FN bool v3_begin_unit(V3Lane &L, const V3Const &c, const u64 *q_code, u32 qle
 		L.pos = rec[32], L.ls = rec[33], L.lq = rec[34], L.ll = rec[35], L.paired = rec[36];
 		L.b_pos = c_end, L.b_ls = L.b_lq = L.b_ll = L.b_paired = 0;
 		L.a_true = 1;
-		L.c_end = (u32)(end2 < qlen ? end2 : qlen);
+		L.c_end = qlen;
 	}
 	return true;
 }
@@ -379,28 +381,36 @@ V3_FN bool v3_begin_unit(V3Lane &L, const V3Const &c, const u64 *q_code, u32 qle
 template <int PHASE>
 V3_FN void v3_finish_unit(const V3Lane &L, u32 *rec, const u32 *col) {
 	const u32 base = PHASE == 1 ? 0u : 16u;
-	const bool keep = PHASE == 1 || L.flag != 0u;  // a boundary that did not synchronise contributes nothing
 #pragma unroll
 	for (int x = 0; x < 16; x++) {
 		u32 v = col[x * V3_CELL_STRIDE];
 		if (x == 0 || x == 5 || x == 10 || x == 15) v += L.sumq;
 		if (x == 15) v += L.sumr;
-		rec[base + x] = keep ? v : 0u;
+		rec[base + x] = v;
 	}
 	if (PHASE == 1) {
 		rec[32] = L.pos, rec[33] = L.ls, rec[34] = L.lq, rec[35] = L.ll, rec[36] = L.paired;
 	} else {
 		rec[37] = L.flag;
+		if (!L.flag) {
+			// the chains reached the end of the query apart: the state the chain of chunk c ends in
+			// replaces E_c (this unit was its only reader); the lowest such chunk of a pair carries
+			// the pair's true final state (src/process.c:199-211 needs it)
+			const bool a = L.a_true != 0u;
+			rec[32] = a ? L.pos : L.b_pos, rec[33] = a ? L.ls : L.b_ls, rec[34] = a ? L.lq : L.b_lq, rec[35] = a ? L.ll : L.b_ll;
+			rec[36] = a ? L.paired : L.b_paired;
+		}
 	}
 }
 
 // Requests V3_SVC_COOP (a bucket: L.cand_p = first SA index, L.cand2 = number of suffixes) and
 // V3_SVC_COOP2 (the two suffixes L.cand_p, L.cand2 of a tag-2 entry): every candidate is compared with
 // the query at pos_Q TO THE END of its match, however long; the longest is the match, unique if no
-// other is as long (process.c:117-122). Result as the lean scan leaves it: job RESOLVED, cand_p = a
+// other is as long (process.c:117-122). Result: job RESOLVED (accounted in the lane's next trip), cand_p = a
 // best candidate, len1 = its length, cand2 = unique. Inside repeats (IS elements, rRNA operons) every
 // directory lookup lands here; the generic step (one lane, binary search with kilobase compares) took
-// about 10 us for each, which made a pool with realistic repeats 2.3 times slower than one without.
+// about 10 us for each. (A per-lane scan of small buckets, one candidate after the other, was slower than
+// this even on repeat-free pools: two dependent loads per candidate while the whole warp waits.)
 // This is the serial form (the emulation, and the specification of the kernel's warp-wide form
 // v3_coop_scan in walk_v3.cuh: one candidate per lane, all growing together).
 V3_FN void v3_scan_full(V3Lane &L, const V3Const &c) {
@@ -432,37 +442,6 @@ V3_FN void v3_scan_full(V3Lane &L, const V3Const &c) {
 //   v3_begin_unit; false = no work in this unit); void slow_step(V3Lane &, u32 *col, u32 sign).
 template <int PHASE, bool QUARTER, class Env>
 V3_FN void v3_service(V3Lane &L, const V3Const &c, Env &env, u32 *col, const V3Pend &P) {
-	if (L.svc == V3_SVC_SCAN) {
-		// a bucket of three or more suffixes (L.cand_p = first SA index, L.cand2 = their number):
-		// compare each with the query through one 64-column window; the longest is the match,
-		// unique if no other is as long (process.c:117-122). Repeats longer than a window and big
-		// buckets are left to the generic step.
-		const u32 first = L.cand_p, count = L.cand2, rem = L.qlen - L.pos;
-		u32 best = 0, best_p = 0, best_n = 0;
-		bool ok = count <= V3_SCAN_MAX;
-		u64 q0, q1;
-		v3_window64(L.q_code, L.pos, q0, q1);
-		for (u32 k = 0; ok && k < count; k++) {
-			const u32 p = v3_ld_sa(c.SA + first + k);
-			u64 s0, s1;
-			v3_window64(c.s_code, p, s0, s1);
-			const u32 D = v3_first_diff(q0 ^ s0, q1 ^ s1);
-			const u32 run = p < c.mid ? c.mid - p : (p == c.mid ? 0u : c.N - p), lim = rem < run ? rem : run;
-			ok = D < 64u || D >= lim;
-			const u32 m = D < lim ? D : lim;
-			best_n = m > best ? 1u : (m == best ? best_n + 1u : best_n);
-			best_p = m > best ? p : best_p;
-			best = m > best ? m : best;
-		}
-		if (ok) {
-			L.cand_p = best_p, L.len1 = best, L.cand2 = best_n == 1u ? 1u : 0u, L.job = V3_RESOLVED, L.svc = V3_RUN;
-			return;
-		}
-		L.svc = V3_SVC_COOP;  // a candidate runs past the window (a repeat): compared to its end by the whole warp
-#ifdef V3_COOP_IN_WARP_LOOP
-		return;	 // ... at the next service stop (the kernel's warp loop serves these requests itself)
-#endif
-	}
 #ifndef V3_COOP_IN_WARP_LOOP
 	if (L.svc == V3_SVC_COOP || L.svc == V3_SVC_COOP2) {
 		v3_scan_full(L, c);
