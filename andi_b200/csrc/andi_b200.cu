@@ -63,6 +63,7 @@ struct andi_ctx {
 		// hist has four zero entries in front (hist_alloc): hist - 1 is then the array of bucket starts
 		// once the scatter has turned hist into the array of bucket ends
 		u32 *hist_alloc = nullptr, *hist = nullptr, *bstart = nullptr, *grp = nullptr, *rank = nullptr, *flags = nullptr;
+		u32 *deep = nullptr;  // sa_bucket.cuh, TieSink: listed buckets (pairs), then listed LCP slots
 		unsigned char *amb = nullptr;
 		unsigned long long *scan_state = nullptr;  // k_scan_buckets: one word per tile + the ticket counter
 		size_t kmers_cap = 0, n_cap = 0;
@@ -258,7 +259,7 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	dfree(ctx, ctx->pool_code), dfree(ctx, ctx->pool_spec), dfree(ctx, ctx->stage_chars);
 	dfree(ctx, ctx->bs.hist_alloc), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
 	dfree(ctx, ctx->bs.scan_state);
-	dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter), dfree(ctx, ctx->walk_bad);
+	dfree(ctx, ctx->bs.deep), dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter), dfree(ctx, ctx->walk_bad);
 	dfree(ctx, ctx->bs.pl_key[0]), dfree(ctx, ctx->bs.pl_key[1]), dfree(ctx, ctx->bs.pl_idx[0]), dfree(ctx, ctx->bs.pl_idx[1]);
 	dfree(ctx, ctx->bs.fvalid);
 	if (ctx->bs.pl_tmp) cudaFreeAsync(ctx->bs.pl_tmp, ctx->stream);

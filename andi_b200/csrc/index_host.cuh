@@ -14,6 +14,8 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #define ANDI_LCP_DIRECT_CAP 1024u
+#define ANDI_DEEP_LIST 65536u		// buckets k_sort_deep can take (sa_bucket.cuh, TieSink)
+#define ANDI_DEEP_LCP_LIST 524288u	// LCP values k_lcp_deep can take
 
 struct MaxOp {
 	__host__ __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a > b ? a : b; }
@@ -261,7 +263,8 @@ static int esa_ensure(andi_ctx *ctx, andi_esa *E) {
 
 static int scratch_ensure(andi_ctx *ctx, size_t kmers, size_t N) {
 	auto &b = ctx->bs;
-	if (!b.flags) CK(dalloc(ctx, &b.flags, 4));
+	if (!b.flags) CK(dalloc(ctx, &b.flags, 8));
+	if (!b.deep) CK(dalloc(ctx, &b.deep, 2 * (size_t)ANDI_DEEP_LIST + ANDI_DEEP_LCP_LIST));
 	if (kmers > b.kmers_cap) {
 		dfree(ctx, b.hist_alloc), dfree(ctx, b.bstart), dfree(ctx, b.scan_state);
 		CK(dalloc(ctx, &b.hist_alloc, kmers + 1 + 4));
@@ -347,7 +350,8 @@ static int build_index_bucket(andi_ctx *ctx, andi_esa *E) {
 		if (rc) return rc;
 	}
 rebuild:
-	CK(cudaMemsetAsync(b.flags, 0, 4 * sizeof(u32), st));
+	CK(cudaMemsetAsync(b.flags, 0, 8 * sizeof(u32), st));
+	const TieSink sink{b.flags, sep ? nullptr : b.deep, ANDI_DEEP_LIST, ANDI_DEEP_LCP_LIST};
 	PaddedList pl{b.pl_key[0], b.pl_idx[0], b.flags + 2, (u32)b.pl_cap};
 	if (sep) {	// unused list slots sort to the end
 		CK(cudaMemsetAsync(b.pl_key[0], 0xff, b.pl_cap * sizeof(u64), st));
@@ -400,7 +404,7 @@ rebuild:
 		k_part_scatter<<<ctas, 1024, parts * sizeof(u32), st>>>(rs, K, K2, per_cta, hist1, b.grp);
 		presence_layout(E);
 		CK(cudaMemsetAsync(E->present.bits + E->present.offset[K - 1], 0, ((((size_t)1 << (2 * (K - 1))) + 31) / 32) * sizeof(u32), st));
-		k_part_sort<<<parts, 1024, bins * sizeof(u32) + 128, st>>>(rs, K, K2, start1, b.grp, E->SA, b.hist, E->dir, b.flags,
+		k_part_sort<<<parts, 1024, bins * sizeof(u32) + 128, st>>>(rs, K, K2, start1, b.grp, E->SA, b.hist, E->dir, sink,
 																	 E->present.bits + E->present.offset[K - 1]);
 		bend = b.hist;	// bucket ends; hist - 1 = bucket starts (hist_alloc holds zeros in front)
 		slots = true, sorted = true;
@@ -441,13 +445,18 @@ rebuild:
 	if (sep) {
 		rc = padded_finish(ctx, E, rs);
 		if (rc) return rc;
-		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, b.flags, atomic_path, present_top);
-		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
+		k_bucket_sort<true><<<nblocks(kmers, 128), 128, 0, st>>>(rs, K, b.bstart, bend, fvalid, E->SA, E->dir, sink, atomic_path, present_top);
+		k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, sink);
 	} else {
 		// (texts without separators: the counting-sort path sorts its buckets with one thread per
 		// slot, the two-level path has sorted them inside k_part_sort already)
-		if (!sorted) k_bucket_sort_slots<<<nblocks(N, 128), 128, 0, st>>>(rs, K, b.hist, E->SA, E->dir, b.flags, present_top);
-		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
+		if (!sorted) k_bucket_sort_slots<<<nblocks(N, 128), 128, 0, st>>>(rs, K, b.hist, E->SA, E->dir, sink, present_top);
+		// the buckets and, below, the LCP values that met a repeat: listed, finished by one warp each
+		// (two small launches that find empty lists on repeat-free texts)
+		k_sort_deep<<<2 * ctx->sm_count, 256, 0, st>>>(rs, E->SA, sink);
+		k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, sink);
+		k_lcp_deep<<<2 * ctx->sm_count, 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, sink);
+		ctx->st.esa_launches += 2;
 	}
 	ctx->st.esa_launches += 2;
 	u32 h_flags[4] = {0, 0, 0, 0};
@@ -477,10 +486,13 @@ rebuild:
 		rc = doubling_rounds(ctx, E, b.grp, b.rank, b.amb, (u32)K);
 		if (!rc) {
 			CK(cudaMemsetAsync(b.flags + 1, 0, sizeof(u32), st));
-			if (E->has_sep)
-				k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
-			else
-				k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, b.flags + 1);
+			CK(cudaMemsetAsync(b.flags + 5, 0, sizeof(u32), st));
+			if (E->has_sep) {
+				k_lcp_direct<true><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, sink);
+			} else {
+				k_lcp_direct<false><<<nblocks((size_t)N + 1, 256), 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, sink);
+				k_lcp_deep<<<2 * ctx->sm_count, 256, 0, st>>>(rs, E->SA, ANDI_LCP_DIRECT_CAP, E->LCP, sink);
+			}
 			ctx->st.esa_launches++;
 			CK(cudaMemcpyAsync(h_flags, b.flags, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));

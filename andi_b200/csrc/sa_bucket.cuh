@@ -22,6 +22,27 @@
 
 #define ANDI_SORT_MAX 16   // buckets up to this size are sorted by one thread
 #define ANDI_SORT_CAP 128  // characters compared before two suffixes are declared tied
+// Buckets the capped per-thread sort cannot finish (suffixes that agree on ANDI_SORT_CAP characters, or
+// more than ANDI_SORT_MAX of them) go to a list and are sorted by one warp each with compares to the
+// end (k_sort_deep): that is where the repeats of real genomes (IS elements, rRNA operons: a few
+// dozen copies, kilobases long) end up. Whatever does not fit -- too many such buckets, a bucket
+// beyond ANDI_DEEP_BUCKET, a match beyond ANDI_DEEP_CAP (tandem repeats, poly-A) -- raises flags[0]
+// and takes the prefix-doubling rounds as before.
+#define ANDI_DEEP_BUCKET 64u
+#define ANDI_DEEP_CAP 16384u
+struct TieSink {
+	u32 *flags;	 // [0] suffixes left tied (-> doubling rounds), [1] LCP values left capped (-> phi), [4] / [5] list lengths
+	u32 *deep;	 // (first slot, end slot) of the listed buckets; behind them the slots of the listed LCP values
+	u32 deep_cap, lcp_cap;
+};
+// true = listed; false = no room (or no list: join mode), the caller reports the ties the old way
+__device__ __forceinline__ bool deep_append(const TieSink &t, u32 b, u32 e) {
+	if (!t.deep || e - b > ANDI_DEEP_BUCKET) return false;
+	const u32 at = atomicAdd(t.flags + 4, 1u);
+	if (at >= t.deep_cap) return false;
+	t.deep[2 * at] = b, t.deep[2 * at + 1] = e;
+	return true;
+}
 
 // Number of leading nucleotides of the suffix at p (capped at 32) and its padded key.
 __device__ __forceinline__ u32 padded_key(const TextView &rs, u32 p, int K, u32 &run) {
@@ -205,14 +226,14 @@ __global__ void k_padded_place(int K, const u64 *__restrict__ key, const u32 *__
 // with a neighbour; their groups are materialised by k_bucket_groups only when there are any.
 template <bool SPEC>
 __device__ __forceinline__ u32 bucket_sort_range(const TextView &rs, int K, u32 key, u32 b, u32 e, bool presorted_front,
-												 u32 *__restrict__ SA, u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous);
+												 u32 *__restrict__ SA, u64 *__restrict__ dir64, const TieSink &sink);
 
 // One bucket, found through the tables of the bucketing pass: [bstart[key], bend[key]).
 template <bool SPEC>
 __device__ __forceinline__ u32 bucket_sort_key(const TextView &rs, int K, u32 key, const u32 *__restrict__ bstart,
 											   const u32 *__restrict__ bend, const u32 *__restrict__ fvalid,
 											   u32 *__restrict__ SA, u64 *__restrict__ dir64,
-											   u32 *__restrict__ n_ambiguous, u32 empty_known) {
+											   const TieSink &sink, u32 empty_known) {
 	const u32 e = bend[key];
 	if (e == bstart[key]) {
 		// first + count is the END of the bucket for every key, so the start of bucket k is the
@@ -222,13 +243,14 @@ __device__ __forceinline__ u32 bucket_sort_key(const TextView &rs, int K, u32 ke
 		return 0;
 	}
 	// fvalid given: the padded suffixes already stand sorted in [bstart, fvalid) (k_padded_place)
-	return bucket_sort_range<SPEC>(rs, K, key, fvalid ? min(fvalid[key], e) : bstart[key], e, fvalid != nullptr, SA, dir64, n_ambiguous);
+	return bucket_sort_range<SPEC>(rs, K, key, fvalid ? min(fvalid[key], e) : bstart[key], e, fvalid != nullptr, SA, dir64, sink);
 }
 
 // Order the suffixes SA[b, e) of one bucket (b < e unless presorted_front) and emit its directory entry.
 template <bool SPEC>
 __device__ __forceinline__ u32 bucket_sort_range(const TextView &rs, int K, u32 key, u32 b, u32 e, bool presorted_front,
-												 u32 *__restrict__ SA, u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous) {
+												 u32 *__restrict__ SA, u64 *__restrict__ dir64, const TieSink &sink) {
+	u32 *n_ambiguous = sink.flags;
 	const bool fvalid = presorted_front;
 	const u32 s = e - b;
 	if (fvalid && s > ANDI_SORT_MAX) {	// valid suffixes only: one group of depth K for the doubling rounds
@@ -261,7 +283,9 @@ __device__ __forceinline__ u32 bucket_sort_range(const TextView &rs, int K, u32 
 			}
 			SA[y] = cur;
 		}
-		if (valid > 1) atomicAdd(n_ambiguous, valid);
+		// a few dozen suffixes: k_sort_deep orders the whole bucket (should it give up, the bucket is
+		// still in the form the doubling rounds expect)
+		if (valid > 1 && !(!SPEC && deep_append(sink, b, e))) atomicAdd(n_ambiguous, valid);
 		dir64[key] = (u64)front | ((u64)valid << 32);
 		return valid;
 	}
@@ -278,7 +302,7 @@ __device__ __forceinline__ u32 bucket_sort_range(const TextView &rs, int K, u32 
 			if (!fvalid) valid += (u32)!is_padded<SPEC>(rs, p1, K);
 			int c = compare_suffixes<SPEC>(rs, p0, p1, ANDI_SORT_CAP);
 			if (c > 0) SA[b] = p1, SA[b + 1] = p0;
-			if (c == 0) atomicAdd(n_ambiguous, 2u);
+			if (c == 0 && !(!SPEC && deep_append(sink, b, e))) atomicAdd(n_ambiguous, 2u);
 		}
 		dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
 		return valid;
@@ -303,7 +327,7 @@ __device__ __forceinline__ u32 bucket_sort_range(const TextView &rs, int K, u32 
 		if (s > 1) SA[b + x] = p;
 		if (x > 0 && compare_suffixes<SPEC>(rs, v[x - 1], p, ANDI_SORT_CAP) == 0) tied++;
 	}
-	if (tied) atomicAdd(n_ambiguous, tied + 1);
+	if (tied && !(!SPEC && deep_append(sink, b, e))) atomicAdd(n_ambiguous, tied + 1);
 	dir64[key] = (u64)(e - valid) | ((u64)valid << 32);
 	return valid;
 }
@@ -314,10 +338,10 @@ __device__ __forceinline__ u32 bucket_sort_range(const TextView &rs, int K, u32 
 template <bool SPEC>
 __global__ void k_bucket_sort(TextView rs, int K, const u32 *__restrict__ bstart, const u32 *__restrict__ bend,
 							  const u32 *__restrict__ fvalid, u32 *__restrict__ SA, u64 *__restrict__ dir64,
-							  u32 *__restrict__ n_ambiguous, u32 empty_known, u32 *__restrict__ present_top) {
+							  const TieSink sink, u32 empty_known, u32 *__restrict__ present_top) {
 	u32 key = blockIdx.x * blockDim.x + threadIdx.x;
 	u32 count = 0;
-	if (key < (1u << (2 * K))) count = bucket_sort_key<SPEC>(rs, K, key, bstart, bend, fvalid, SA, dir64, n_ambiguous, empty_known);
+	if (key < (1u << (2 * K))) count = bucket_sort_key<SPEC>(rs, K, key, bstart, bend, fvalid, SA, dir64, sink, empty_known);
 	u32 m = __ballot_sync(0xffffffffu, count != 0);
 	if ((threadIdx.x & 31u) == 0 && m) {
 		m |= m >> 1, m |= m >> 2;  // bit 4g = any of the four k-mers of group g
@@ -346,13 +370,13 @@ __device__ __forceinline__ u32 padded_key_nosep(const TextView &rs, u32 p, int K
 }
 
 __global__ void k_bucket_sort_slots(TextView rs, int K, const u32 *__restrict__ bend, u32 *__restrict__ SA, u64 *__restrict__ dir64,
-									u32 *__restrict__ n_ambiguous, u32 *__restrict__ present_top) {
+									const TieSink sink, u32 *__restrict__ present_top) {
 	const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= rs.len) return;
 	// the bucket of the suffix in this slot: [bend[key - 1], bend[key]) (bend[-1] is a zero in front of the table)
 	const u32 key = padded_key_nosep(rs, SA[j], K);
 	if (bend[(int)key - 1] != j) return;  // not the head of its bucket
-	const u32 count = bucket_sort_range<false>(rs, K, key, j, bend[key], false, SA, dir64, n_ambiguous);
+	const u32 count = bucket_sort_range<false>(rs, K, key, j, bend[key], false, SA, dir64, sink);
 	if (count) {
 		const u32 y = key >> 2;	 // its (K-1)-mer
 		atomicOr(present_top + (y >> 5), 1u << (y & 31u));
@@ -510,7 +534,7 @@ __global__ void __launch_bounds__(1024) k_part_scatter(TextView rs, int K, int K
 // start1[x] = first slot of part x (x = blockIdx.x), start1[x + 1] its end. bend[key] = end of bucket key.
 __global__ void __launch_bounds__(1024) k_part_sort(TextView rs, int K, int K2, const u32 *__restrict__ start1,
 													 const u32 *__restrict__ tmp, u32 *__restrict__ SA, u32 *__restrict__ bend,
-													 u64 *__restrict__ dir64, u32 *__restrict__ n_ambiguous,
+													 u64 *__restrict__ dir64, const TieSink sink,
 													 u32 *__restrict__ present_top) {
 	extern __shared__ u32 sh[];	 // 4^K2 counters, then 32 warp sums
 	const u32 bins = 1u << (2 * K2), mask = bins - 1u, part = blockIdx.x;
@@ -557,7 +581,7 @@ __global__ void __launch_bounds__(1024) k_part_sort(TextView rs, int K, int K2, 
 		const u32 end = sh[b0 + x];
 		if (end > start) {
 			const u32 key = (u32)(key0 + x);
-			if (bucket_sort_range<false>(rs, K, key, start, end, false, SA, dir64, n_ambiguous))
+			if (bucket_sort_range<false>(rs, K, key, start, end, false, SA, dir64, sink))
 				atomicOr(present_top + ((key >> 2) >> 5), 1u << ((key >> 2) & 31u));
 		}
 		start = end;
@@ -577,6 +601,46 @@ __global__ void __launch_bounds__(1024) k_part_sort(TextView rs, int K, int K2, 
 //   tag 3 (three or more)   low 32 bits = first SA index, bits 32..61 = their number
 // Written by k_prefix_len (esa_kernels.cuh) together with the prefix lengths.
 #define ANDI_FDIR_TAG(e) ((u32)((e) >> 62))
+
+// One warp per listed bucket [b, e) (at most ANDI_DEEP_BUCKET suffixes): every suffix is ranked by
+// counting the bucket members below it, compares running to the end of the match (cap: ANDI_DEEP_CAP
+// characters; a compare that gets there raises flags[0] and everybody stops: the doubling rounds
+// take over). Texts without separators.
+__global__ void __launch_bounds__(256) k_sort_deep(TextView rs, u32 *__restrict__ SA, const TieSink sink) {
+	const u32 lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	const u32 n = min(*(volatile u32 *)(sink.flags + 4), sink.deep_cap);
+	for (u32 x = warp; x < n; x += nwarps) {
+		if (*(volatile u32 *)sink.flags) return;  // somebody met a match beyond the cap
+		const u32 b = sink.deep[2 * x], m = sink.deep[2 * x + 1] - b;
+		u32 p[ANDI_DEEP_BUCKET / 32], r[ANDI_DEEP_BUCKET / 32];
+		bool capped = false;
+#pragma unroll
+		for (u32 k = 0; k < ANDI_DEEP_BUCKET / 32; k++) {
+			const u32 i = lane + 32u * k;
+			p[k] = i < m ? SA[b + i] : 0u, r[k] = 0;
+		}
+		for (u32 j = 0; j < m; j++) {
+			const u32 pj = SA[b + j];  // the same word for all lanes
+#pragma unroll
+			for (u32 k = 0; k < ANDI_DEEP_BUCKET / 32; k++) {
+				const u32 i = lane + 32u * k;
+				if (i < m && i != j) {
+					const int c = compare_suffixes<false>(rs, pj, p[k], ANDI_DEEP_CAP);
+					capped |= c == 0;
+					r[k] += c < 0 ? 1u : 0u;
+				}
+			}
+		}
+		if (__any_sync(0xffffffffu, capped)) {
+			if (lane == 0) atomicAdd(sink.flags, m);
+			return;	 // (the bucket stays as it was: a permutation of its suffixes)
+		}
+		__syncwarp();  // all reads of SA[b, e) are done
+#pragma unroll
+		for (u32 k = 0; k < ANDI_DEEP_BUCKET / 32; k++)
+			if (lane + 32u * k < m) SA[b + r[k]] = p[k];
+	}
+}
 
 // Only when k_bucket_sort reported ties: group heads, ranks and "ambiguous" flags of every
 // suffix, the input of the doubling rounds (index_host.cuh). Buckets are laid out as
@@ -623,8 +687,7 @@ __global__ void k_bucket_groups(TextView rs, int K, const u32 *__restrict__ bsta
 // the cap raise *overflow and the caller recomputes everything through the phi array
 // (src/esa.c:373-426, k_phi / k_plcp) -- only repeat-rich texts get there.
 template <bool SPEC>
-__global__ void k_lcp_direct(TextView rs, const u32 *__restrict__ SA, u32 cap, int32_t *__restrict__ LCP,
-							 u32 *__restrict__ overflow) {
+__global__ void k_lcp_direct(TextView rs, const u32 *__restrict__ SA, u32 cap, int32_t *__restrict__ LCP, const TieSink sink) {
 	u32 j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j > rs.len) return;
 	if (j == 0 || j == rs.len) {
@@ -634,6 +697,46 @@ __global__ void k_lcp_direct(TextView rs, const u32 *__restrict__ SA, u32 cap, i
 	u32 a = SA[j - 1], b = SA[j];
 	u32 lim = min(cap, SPEC ? rs.len - max(a, b) : pair_limit_fast(rs, a, b));
 	u32 m = match_len<SPEC>(rs, a, rs, b, lim);
-	if (m == cap) atomicExch(overflow, 1u);
+	if (m == cap) {
+		// the value goes on from here in k_lcp_deep if the list has room (texts without separators)
+		const u32 at = (!SPEC && sink.deep) ? atomicAdd(sink.flags + 5, 1u) : 0xffffffffu;
+		if (at < sink.lcp_cap)
+			sink.deep[2 * sink.deep_cap + at] = j;
+		else
+			atomicExch(sink.flags + 1, 1u);
+	}
 	LCP[j] = (int32_t)m;
+}
+
+// The listed LCP values (they reached the cap of k_lcp_direct: neighbours inside a repeat), one warp
+// each: 32 windows of 64 characters per round, on to the first mismatch or the limit.
+__global__ void __launch_bounds__(256) k_lcp_deep(TextView rs, const u32 *__restrict__ SA, u32 cap, int32_t *__restrict__ LCP,
+												   const TieSink sink) {
+	const u32 lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	if (*(volatile u32 *)(sink.flags + 1)) return;	// the list overflowed: everything is redone through phi
+	const u32 n = min(*(volatile u32 *)(sink.flags + 5), sink.lcp_cap);
+	for (u32 x = warp; x < n; x += nwarps) {
+		const u32 j = sink.deep[2 * sink.deep_cap + x];
+		const u32 a = SA[j - 1], b = SA[j], lim = pair_limit_fast(rs, a, b);
+		u32 m = cap;
+		while (m < lim) {
+			const u32 at = m + 64u * lane;
+			u32 d = 64u;
+			if (at < lim) {
+				u64 a0, a1, b0, b1;
+				window64(rs.code, a + at, a0, a1);
+				window64(rs.code, b + at, b0, b1);
+				const u64 x0 = a0 ^ b0, x1 = a1 ^ b1;
+				d = x0 ? (u32)(__ffsll((long long)x0) - 1) >> 1 : (x1 ? 32u + ((u32)(__ffsll((long long)x1) - 1) >> 1) : 64u);
+			}
+			const unsigned hit = __ballot_sync(0xffffffffu, d < 64u);
+			if (hit) {
+				const int first = __ffs((int)hit) - 1;
+				m += 64u * (u32)first + __shfl_sync(0xffffffffu, d, first);
+				break;
+			}
+			m += 2048u;
+		}
+		if (lane == 0) LCP[j] = (int32_t)min(m, lim);
+	}
 }

@@ -52,6 +52,8 @@ def stress_sequences():
     for i in range(12):
         g[3000 + 2900 * i : 3700 + 2900 * i] = g[1000:1700]
     g[36500:39500] = g[500:3500]
+    for i in range(24):  # ... and a short one in 24 copies: buckets beyond what one thread sorts (index build)
+        g[2200 + 1450 * i : 2500 + 1450 * i] = g[100:400]
     out["copies"] = [synth.ACGT[synth.mutate(g, p, seed=40 + k)].tobytes() for k, p in enumerate((0.0, 0.01, 0.03))]
     unrelated = synth.star_phylogeny(1, 20000, [0.0], seed=99)[0]
     out["unrelated"] = [base[0], unrelated]
