@@ -159,7 +159,7 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 		u32 nbad = 0, first = nq;
 		for (u32 k = 0; k < nq; k++)
 			if (bad[k]) nbad++, first = first == nq ? k : first;
-		fprintf(stderr, "[andi_b200] subject %u: %u of %u pairs with a boundary that did not synchronise\n", S.self, nbad, nq);
+		fprintf(stderr, "[andi_b200] subject %u: %u of %u pairs with a boundary whose chains did not meet (k_walk_v3: before the end of the query; else: inside the next chunk)\n", S.self, nbad, nq);
 		if (first < nq) {
 			std::vector<u32> rec((size_t)plan.cpq * ANDI_UNIT_WORDS);
 			CK(cudaMemcpy(rec.data(), d_records + (size_t)first * plan.cpq * ANDI_UNIT_WORDS, rec.size() * sizeof(u32), cudaMemcpyDeviceToHost));

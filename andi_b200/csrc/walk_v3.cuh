@@ -43,12 +43,59 @@ V3_FN void v3_count_slice(const V3Lane &L, const V3Const &c, u32 *col, u32 sign)
 #define V3_COOP_IN_WARP_LOOP 1  // requests V3_SVC_COOP / V3_SVC_COOP2 are served by v3_coop_scan below, not by v3_service
 #include "walk_v3_lane.h"
 
-// v3_scan_full (walk_v3_lane.h) by the whole warp: the requests of the lanes in `want`, one after the
-// other; every lane takes one candidate of the request (32 per round) and all candidates grow
-// together, one 64-column window per iteration, until the last of them has met its first mismatch
-// or its limit. Called with all 32 lanes.
+// v3_scan_full (walk_v3_lane.h) by the whole warp: the requests of the lanes in `want`; every lane
+// takes one candidate (requests of up to eight candidates: four requests at a time, eight lanes each;
+// larger buckets: one request at a time, 32 candidates per round) and all candidates grow together,
+// one 64-column window per iteration, until the last of them has met its first mismatch or its
+// limit. Called with all 32 lanes.
 V3_FN void v3_coop_scan(V3Lane &L, const V3Const &c, unsigned want) {
 	const u32 lane = threadIdx.x & 31u;
+	// Requests with at most eight candidates (most buckets of three or more, every tag-2 pair) are
+	// served FOUR AT A TIME, eight lanes each: where such buckets are common (5 Mbp genomes at K = 12,
+	// divergent pairs with many lookups) several lanes of a warp ask at every service stop, and one
+	// request after the other cost more than it saved there.
+	unsigned small = __ballot_sync(0xffffffffu, ((want >> lane) & 1u) && (L.svc == V3_SVC_COOP2 || L.cand2 <= 8u));
+	want &= ~small;
+	while (small) {
+		const u32 g = lane >> 3, sub = lane & 7u;
+		const u32 r = __fns(small, 0u, (int)g + 1);	 // the request lane my group works for (0xffffffff: none)
+		const bool has = r != 0xffffffffu;
+		const u32 src = has ? r : 0u;
+		const bool two = __shfl_sync(0xffffffffu, L.svc, src) == V3_SVC_COOP2;
+		const u32 a = __shfl_sync(0xffffffffu, L.cand_p, src), b = __shfl_sync(0xffffffffu, L.cand2, src);
+		const u32 pos = __shfl_sync(0xffffffffu, L.pos, src), qlen = __shfl_sync(0xffffffffu, L.qlen, src);
+		const u64 *q_code = reinterpret_cast<const u64 *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(L.q_code), src));
+		const bool have = has && sub < (two ? 2u : b);
+		u32 p = 0;
+		if (have) p = two ? (sub ? b : a) : __ldg(c.SA + a + sub);
+		const u32 run = p < c.mid ? c.mid - p : (p == c.mid ? 0u : c.N - p), rem = qlen - pos;
+		const u32 lim = have ? (rem < run ? rem : run) : 0u;
+		u32 len = 0;
+		bool alive = len < lim;
+		while (__any_sync(0xffffffffu, alive)) {
+			if (alive) {
+				u64 q0, q1, s0, s1;
+				window64(q_code, pos + len, q0, q1);
+				window64(c.s_code, p + len, s0, s1);
+				const u32 D = v3_first_diff(q0 ^ s0, q1 ^ s1);
+				len += D < lim - len ? D : lim - len;
+				alive = D >= 64u && len < lim;
+			}
+		}
+		u32 top = have ? len : 0u;
+		top = max(top, __shfl_xor_sync(0xffffffffu, top, 1));
+		top = max(top, __shfl_xor_sync(0xffffffffu, top, 2));
+		top = max(top, __shfl_xor_sync(0xffffffffu, top, 4));
+		const unsigned at_top = __ballot_sync(0xffffffffu, have && len == top) & (0xffu << (8u * g));
+		const u32 n = (u32)__popc(at_top), p_top = __shfl_sync(0xffffffffu, p, at_top ? __ffs((int)at_top) - 1 : 0);
+		// the result travels from lane 0 of the group to the lane that asked
+		const u32 my_g = (u32)__popc(small & ((1u << lane) - 1u));
+		const bool served = ((small >> lane) & 1u) && my_g < 4u;
+		const u32 from = served ? 8u * my_g : 0u;
+		const u32 r_top = __shfl_sync(0xffffffffu, top, from), r_n = __shfl_sync(0xffffffffu, n, from), r_p = __shfl_sync(0xffffffffu, p_top, from);
+		if (served) L.cand_p = r_p, L.len1 = r_top, L.cand2 = r_n == 1u ? 1u : 0u, L.job = V3_RESOLVED, L.svc = V3_RUN;
+		for (int k = 0; k < 4 && small; k++) small &= small - 1u;
+	}
 	while (want) {
 		const int r = __ffs((int)want) - 1;
 		want &= want - 1u;
