@@ -1,30 +1,9 @@
 #!/bin/bash
-# sub-warp cooperative scan: full GPU suite first (stop on failure), then the final legs that depend on the walk kernel
-python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_tests.log 2>&1; tail -3 gpurun_out/r2_gpu_tests.log
-grep -q " passed" gpurun_out/r2_gpu_tests.log && ! grep -q "failed" gpurun_out/r2_gpu_tests.log || exit 1
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-200
-B="--steps 3 --warmup 3 --no-cpu --no-e2e --no-full"
-python bench.py --workload c3 $B 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c3_kimura.json
-python bench.py --workload c3 --model LOGDET $B 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c3_logdet.json
-python bench.py --workload c2 $B 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c2.json
-python bench.py --workload c2 --repeats 30 $B 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c2_repeats.json
-python bench.py --repeats 30 $B 2>/dev/null | grep '^{' > gpurun_out/r2_bench_c4_repeats.json
-python bench.py --genomes 512 --repeats 30 $B 2>/dev/null | grep '^{' > gpurun_out/r2_bench_512_repeats.json
-python bench.py --genomes 512 $B 2>/dev/null | grep '^{' > gpurun_out/r2_bench_512.json
-tools/capture_traffic.sh r2 > /dev/null
-python tools/ncu_summary.py gpurun_out/r2_walk.ncu-rep > gpurun_out/r2_walk_ncu_summary.txt
-ncu -i gpurun_out/r2_walk.ncu-rep --page source --csv --print-source sass > gpurun_out/r2_walk_source.csv 2>/dev/null
-python tools/ncu_regions.py gpurun_out/r2_walk_source.csv "k_walk_v3<(int)1" > gpurun_out/r2_walk_regions.txt
-cp gpurun_out/walk_traffic.json profiles/walk_traffic.json
-python bench.py --steps 4 --warmup 3 2> gpurun_out/r2_bench_n1.err | grep '^{' > gpurun_out/r2_bench_n1.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_repeats.csv python bench.py --genomes 512 --repeats 30 --steps 1 --warmup 0 --rows 3 --no-cpu --no-e2e --no-full > /dev/null 2>&1
-python tools/launch_summary.py gpurun_out/r2_launches_repeats.csv > gpurun_out/r2_launch_list_repeats_summary.txt
+# 2 GPUs: the multi-device tests (C threads, NCCL ranks, command line) and the bench under torch.distributed.run
+python -m pytest tests/test_gpu_multi.py tests/test_gpu_cli.py -m gpu -x -q 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 4 --warmup 3 2> gpurun_out/r2_bench_n2.err | grep '^{' > gpurun_out/r2_bench_n2.json
 python - <<'PY'
-import json, glob
-for f in sorted(glob.glob("gpurun_out/r2_bench_*.json")):
-    try:
-        d = json.load(open(f))
-    except Exception as e:
-        print(f, "unreadable", e); continue
-    print(f.split("/")[-1], round(d["value"]), round(d["ms_per_step"], 2), d.get("e2e") and round(d["e2e"]["value"]), d.get("roofline") and (d["roofline"]["launch_ms"], d["roofline"]["traffic"], round(d["roofline"]["frac"], 4)), d.get("parity"), d.get("full_matrix") and d["full_matrix"]["seconds"], d.get("esa_build") and round(d["esa_build"]["ms_per_subject"], 3), d.get("cub_calls"))
+import json
+d = json.load(open("gpurun_out/r2_bench_n2.json"))
+print("n2", round(d["value"]), round(d["ms_per_step"], 2), round(d["e2e"]["value"]), d["full_matrix"]["seconds"], d["full_matrix"]["blake2b_of_matrix"], d["full_matrix"]["rows_per_rank"], d.get("parity"))
 PY
