@@ -80,6 +80,10 @@ struct andi_ctx {
 	bool part_attr_set = false;					 // k_part_* may use 64 KB of dynamic shared memory on this device
 	u32 *walk_bad = nullptr;					 // per pair: a chunk boundary did not synchronise (k_walk_reduce_sum)
 	size_t walk_bad_cap = 0;
+	// sum of the anchor lengths the chunk walks of the last launch ended with, and their number
+	// (k_walk_reduce_sum); copied to the host after every walk, looked at before the next one
+	unsigned long long *walk_stat = nullptr, *h_walk_stat = nullptr;
+	bool walk_burst = false;  // launch k_walk_v3<.., BURST = true>: the pool is one of near-identical genomes
 
 	// pinned staging planes of andi_pool_set_host (the pool is packed on the host, host_pack.c)
 	u64 *h_code = nullptr, *h_spec = nullptr;
@@ -259,6 +263,8 @@ extern "C" void andi_ctx_destroy(andi_ctx *ctx) {
 	dfree(ctx, ctx->pool_code), dfree(ctx, ctx->pool_spec), dfree(ctx, ctx->stage_chars);
 	dfree(ctx, ctx->bs.hist_alloc), dfree(ctx, ctx->bs.bstart), dfree(ctx, ctx->bs.grp), dfree(ctx, ctx->bs.rank);
 	dfree(ctx, ctx->bs.scan_state);
+	dfree(ctx, ctx->walk_stat);
+	if (ctx->h_walk_stat) cudaFreeHost(ctx->h_walk_stat);
 	dfree(ctx, ctx->bs.deep), dfree(ctx, ctx->bs.flags), dfree(ctx, ctx->bs.amb), dfree(ctx, ctx->walk_counter), dfree(ctx, ctx->walk_bad);
 	dfree(ctx, ctx->bs.pl_key[0]), dfree(ctx, ctx->bs.pl_key[1]), dfree(ctx, ctx->bs.pl_idx[0]), dfree(ctx, ctx->bs.pl_idx[1]);
 	dfree(ctx, ctx->bs.fvalid);

@@ -23,7 +23,7 @@ typedef uint32_t u32;
 #define V3_SERVE_EVERY 8u
 #define V3_COUNT_STATS 1
 
-enum { ST_trips, ST_ext_trips, ST_cand_trips, ST_steps, ST_lucky_hits, ST_lookups, ST_tag0, ST_tag1, ST_wide_gaps, ST_slow_steps, ST_slow_tail, ST_slow_tag3, ST_wide_pairs, ST_slow_long, ST_cols_trips, ST_pushes, ST_drained, ST_drains, ST_drain_rounds, ST_coop_scans,
+enum { ST_trips, ST_ext_trips, ST_cand_trips, ST_steps, ST_lucky_hits, ST_lookups, ST_tag0, ST_tag1, ST_wide_gaps, ST_slow_steps, ST_slow_tail, ST_slow_tag3, ST_wide_pairs, ST_slow_long, ST_cols_trips, ST_pushes, ST_drained, ST_drains, ST_drain_rounds, ST_coop_scans, ST_ext_rounds, ST_bursts,
 	   ST_warp_trips, ST_running_lanes, ST_services, ST_served_lanes, ST_N };
 static u64 *g_stats = nullptr;
 #define V3_STAT(name)                \
@@ -199,6 +199,21 @@ static void run_phase(Env &env, const V3Const &c, u32 n_warps) {
 			if (most > V3_PEND_SLOTS - 2u) {  // a queue is nearly full: the whole warp classifies what it has queued
 				if (g_stats) g_stats[ST_drains]++, g_stats[ST_drain_rounds] += most;
 				for (u32 x = 0; x < 32; x++) v3_drain_lane(w.lane[x], w.pend(x), w.cells[x]);
+			}
+			auto ext_lanes = [&w]() {
+				u32 n = 0;
+				for (auto &l : w.lane) n += l.svc == V3_RUN && l.job == V3_EXT;
+				return n;
+			};
+			u32 run_now = 0;
+			for (auto &l : w.lane) run_now += l.svc == V3_RUN;
+			if ((w.trip & (V3_BURST_EVERY - 1u)) == 0u && v3_burst_now(ext_lanes(), run_now)) {  // most of the running lanes inside long anchors (walk_v3.cuh)
+				if (g_stats) g_stats[ST_bursts]++;
+				for (u32 r = 0; r < V3_BURST_ROUNDS; r++) {
+					for (auto &l : w.lane)
+						if (l.svc == V3_RUN && l.job == V3_EXT) v3_ext_round(l, c);
+					if (!v3_burst_on(ext_lanes(), run_now)) break;
+				}
 			}
 			running = 0;
 			for (u32 x = 0; x < 32; x++)

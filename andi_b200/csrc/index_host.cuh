@@ -4,9 +4,12 @@
 // Optimistic pipeline, ONE host synchronisation per subject in the common case:
 //   bucket suffix sort (sa_bucket.cuh) -> direct LCP -> k-mer directory / presence / prefix
 //   lengths -> read back two flags {tied suffixes, LCP overflow}.
-// Only when suffixes are still tied (repeats longer than ANDI_SORT_CAP, oversized buckets) do
-// the prefix-doubling rounds run (group, rank[i+h]) with h = K, 2K, ...; only when an LCP value
-// reached the direct cap is the LCP recomputed through the phi array (src/esa.c:373-426).
+// Buckets the capped per-thread sort cannot finish (repeats longer than ANDI_SORT_CAP, 17 to 64
+// suffixes) and LCP values that reach the direct cap are LISTED and finished by one warp each
+// (k_sort_deep, k_lcp_deep: the repeats of real genomes). Only when suffixes are still tied after
+// that (full list, larger buckets, matches beyond ANDI_DEEP_CAP) do the prefix-doubling rounds run
+// (group, rank[i+h]) with h = K, 2K, ...; only when the LCP list overflows (join mode: when any
+// value reached the cap) is the LCP recomputed through the phi array (src/esa.c:373-426).
 // The radix sort / scan / select used by the doubling rounds are CUB device primitives.
 #pragma once
 #include "sa_bucket.cuh"

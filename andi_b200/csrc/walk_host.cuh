@@ -110,7 +110,7 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	int per_sm = 0;
 	const unsigned threads = v3 ? V3_THREADS : ANDI_WALK_THREADS;
 	if (v3)
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quarter ? k_walk_v3<1, true> : k_walk_v3<1, false>, V3_THREADS, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quarter ? k_walk_v3<1, true, false> : k_walk_v3<1, false, false>, V3_THREADS, 0));
 	else
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf, ANDI_WALK_THREADS, 0));
 	if (per_sm < 1) per_sm = 1;
@@ -125,8 +125,18 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 	if (!ctx->walk_counter) CK(dalloc(ctx, &ctx->walk_counter, 2));
 	CK(cudaMemsetAsync(ctx->walk_counter, 0, 2 * sizeof(unsigned long long), ctx->stream));
 	if (v3) {
-		auto p1 = quarter ? k_walk_v3<1, true> : k_walk_v3<1, false>;
-		auto p2 = quarter ? k_walk_v3<2, true> : k_walk_v3<2, false>;
+		// The mean length of the anchors the chunk walks of this lane's previous launch ended with (the
+		// copy has arrived: the index build has synchronised the stream since): kilobases = a pool of
+		// near-identical genomes -> the instantiation with EXT bursts; a few dozen bases -> without.
+		if (ctx->h_walk_stat && ctx->h_walk_stat[1]) {
+			const unsigned long long mean = ctx->h_walk_stat[0] / ctx->h_walk_stat[1];
+			if (mean > 192ULL) ctx->walk_burst = true;
+			if (mean < 128ULL) ctx->walk_burst = false;
+		}
+		if (const char *fb = getenv("ANDI_B200_BURST")) ctx->walk_burst = atoi(fb) != 0;  // experiments only
+		const bool burst = ctx->walk_burst;
+		auto p1 = quarter ? (burst ? k_walk_v3<1, true, true> : k_walk_v3<1, true, false>) : (burst ? k_walk_v3<1, false, true> : k_walk_v3<1, false, false>);
+		auto p2 = quarter ? (burst ? k_walk_v3<2, true, true> : k_walk_v3<2, true, false>) : (burst ? k_walk_v3<2, false, true> : k_walk_v3<2, false, false>);
 		p1<<<grid, V3_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records, ctx->walk_counter);
 		if (plan.cpq > 1)
 			p2<<<grid, V3_THREADS, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records,
@@ -145,9 +155,16 @@ static int launch_walk(andi_ctx *ctx, SubjectIndex S, const QueryView *d_queries
 		ctx->walk_bad_cap = nq;
 	}
 	CK(cudaMemsetAsync(ctx->walk_bad, 0, (size_t)nq * sizeof(u32), ctx->stream));
+	if (!ctx->walk_stat) {
+		CK(dalloc(ctx, &ctx->walk_stat, 2));
+		CK(cudaHostAlloc((void **)&ctx->h_walk_stat, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+		ctx->h_walk_stat[0] = ctx->h_walk_stat[1] = 0;
+	}
+	CK(cudaMemsetAsync(ctx->walk_stat, 0, 2 * sizeof(unsigned long long), ctx->stream));
 	CK(cudaMemsetAsync(d_out, 0, (size_t)nq * 17 * sizeof(u32), ctx->stream));
 	k_walk_reduce_sum<<<dim3(nq, nblocks(plan.cpq, ANDI_REDUCE_SLICE)), 256, 0, ctx->stream>>>(d_queries, d_query_ids, S.self, plan.chunk,
-																								plan.cpq, d_records, d_out, ctx->walk_bad);
+																								plan.cpq, d_records, d_out, ctx->walk_bad, v3 ? ctx->walk_stat : nullptr);
+	if (v3) CK(cudaMemcpyAsync(ctx->h_walk_stat, ctx->walk_stat, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	rf<<<nblocks((size_t)nq * 32, 128), 128, 0, ctx->stream>>>(S, d_queries, d_query_ids, nq, plan.chunk, plan.cpq, threshold, d_records,
 																ctx->walk_bad, d_out, v3 ? 1u : 0u);
 	ctx->st.walk_launches += 1;

@@ -15,6 +15,9 @@
 //   k_walk_reduce  one warp per pair: total = sum_c (U_c + D_c) while every boundary
 //                  synchronised; where one did not (e.g. a long anchor-free stretch) it walks on
 //                  sequentially from the last known true state until the chains meet again.
+//                  (The kernels of this file stop a boundary's replay at the end of chunk c+1.
+//                  k_walk_v3, walk_v3.cuh, lets it run until the chains meet, wherever that is:
+//                  its records need no sequential path -- k_walk_reduce_finish(extended = 1).)
 //
 // All threads of a launch work on ONE subject, so its index (SA, directory, packed text) stays
 // resident in the 126 MB L2 while the queries stream through. The main loop has a single back
@@ -601,7 +604,7 @@ k_walk_reduce(const SubjectIndex S, const QueryView *__restrict__ queries, const
 // caller) = 0xffffffff - c for the first chunk c of pair k whose boundary did not synchronise. Grid: (nq, slices); 256 threads = 8 warps, one record per warp and turn.
 __global__ void __launch_bounds__(256)
 k_walk_reduce_sum(const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 self, u32 chunk, u32 cpq,
-				  const u32 *__restrict__ records, u32 *__restrict__ out, u32 *__restrict__ bad) {
+				  const u32 *__restrict__ records, u32 *__restrict__ out, u32 *__restrict__ bad, unsigned long long *__restrict__ stat) {
 	const u32 k = blockIdx.x, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;	 // grid: (pair, slice)
 	const u32 qid = query_ids ? query_ids[k] : k;
 	if (qid == self) return;
@@ -610,11 +613,18 @@ k_walk_reduce_sum(const QueryView *__restrict__ queries, const u32 *__restrict__
 	const u32 c0 = blockIdx.y * ANDI_REDUCE_SLICE, c1 = min(nch, c0 + ANDI_REDUCE_SLICE);
 	if (c0 >= nch) return;
 	const u32 *base = records + (unsigned long long)k * cpq * ANDI_UNIT_WORDS;
-	u32 sum = 0, first_bad = 0xffffffffu;
+	u32 sum = 0, first_bad = 0xffffffffu, anchor_sum = 0;
 	for (u32 c = c0 + wid; c < c1; c += 8u) {
 		const u32 *rec = base + (unsigned long long)c * ANDI_UNIT_WORDS;
 		sum += rec[lane];												 // lanes 0..15: U_c, lanes 16..31: D_c
 		if (lane == 5u && rec[37] == 0u) first_bad = min(first_bad, c);	 // the flag of the boundary behind chunk c
+		if (lane == 6u) anchor_sum += min(rec[35], 1u << 20);				 // length of the anchor the chunk's walk ended with
+	}
+	// stat[0] += those lengths, stat[1] += chunks: their mean tells the host what kind of pool this is
+	// (a few dozen bases: ordinary divergence; kilobases: near-identical genomes -> k_walk_v3<.., BURST>)
+	if (stat && lane == 6u && c0 + wid < c1) {
+		atomicAdd(stat, (unsigned long long)anchor_sum);
+		atomicAdd(stat + 1, (unsigned long long)((c1 - c0 - wid + 7u) / 8u));
 	}
 	sum += __shfl_down_sync(0xffffffffu, sum, 16);	// lane x < 16: U[x] + D[x]
 	__shared__ u32 part[8][16];

@@ -1,4 +1,4 @@
-// andi_b200/csrc/walk_v3.cuh -- k_walk_v3<PHASE, QUARTER>: the chunked anchor walk for texts without
+// andi_b200/csrc/walk_v3.cuh -- k_walk_v3<PHASE, QUARTER, BURST>: the chunked anchor walk for texts without
 // separators (QUARTER = RAW / JC / KIMURA counting, the headline configuration; else LOGDET / ANI). The per-lane logic, its rationale and
 // its reference citations are in walk_v3_lane.h (the same text runs in the CPU emulation of
 // emu/emu_v3.cpp); this file supplies the device primitives, the warp loop and the launch.
@@ -196,7 +196,11 @@ struct V3Env {
 	}
 };
 
-template <int PHASE, bool QUARTER>
+// BURST: the instantiation for pools of near-identical genomes (v3_ext_round, walk_v3_lane.h); the host
+// picks it per launch from the mean anchor length of the lane's previous walk (walk_host.cuh). Looking
+// for bursts costs the ordinary walk 1.6 % (measured on one box: 565.9 k against 556.8 k pairs/s), so
+// it is not in the instantiation that pool runs.
+template <int PHASE, bool QUARTER, bool BURST>
 __global__ void __launch_bounds__(V3_THREADS, V3_BLOCKS_PER_SM)
 k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32 *__restrict__ query_ids, u32 nq, u32 chunk,
 		  u32 cpq, u32 threshold, u32 *__restrict__ records, unsigned long long *__restrict__ next_unit) {
@@ -233,6 +237,17 @@ k_walk_v3(const SubjectIndex S, const QueryView *__restrict__ queries, const u32
 				__syncwarp();
 			}
 			L.npend = 0;
+		}
+		// most of the warp inside long anchors: their windows back to back, without the trip around them
+		if (BURST) {
+			const u32 run_now = (u32)__popc(running);  // (as of the top of this trip: lanes served since then are not counted)
+			if ((trip & (V3_BURST_EVERY - 1u)) == 0u &&
+				v3_burst_now((u32)__popc(__ballot_sync(0xffffffffu, L.svc == V3_RUN && L.job == V3_EXT)), run_now)) {
+				for (u32 r = 0; r < V3_BURST_ROUNDS; r++) {
+					if (L.svc == V3_RUN && L.job == V3_EXT) v3_ext_round(L, c);
+					if (!v3_burst_on((u32)__popc(__ballot_sync(0xffffffffu, L.svc == V3_RUN && L.job == V3_EXT)), run_now)) break;
+				}
+			}
 		}
 		if (L.svc == V3_RUN) v3_trip<PHASE, QUARTER>(L, c, col, P);
 		__syncwarp();

@@ -329,6 +329,29 @@ V3_FN void v3_trip(V3Lane &L, const V3Const &c, u32 *col, const V3Pend &P) {
 	if (push_n) v3_push_gap(L, P, q0, s0, push_n, sign);
 }
 
+// One more window of a growing anchor (job EXT) outside the trips: what an EXT trip does, and nothing
+// else. Near-identical genomes (outbreak isolates: a few SNPs per megabase) have anchors of tens of
+// kilobases, every unit runs its first one to its end, and a whole trip per 64 columns made such a pool
+// several times slower than a pool of ordinary divergence -- the reference's easiest case. When most of
+// a warp is in EXT (v3_burst_now) the warp takes these rounds back to back instead.
+V3_FN void v3_ext_round(V3Lane &L, const V3Const &c) {
+	const u32 eq = L.lq + L.ll, es = L.ls + L.ll;
+	const u32 erun = es < c.mid ? c.mid - es : (es == c.mid ? 0u : c.N - es), erem = L.qlen - eq;
+	const u32 elim = erem < erun ? erem : erun;
+	u64 a0, a1, b0, b1;
+	v3_window64(L.q_code, eq, a0, a1);
+	v3_window64(c.s_code, es, b0, b1);
+	const u32 E = v3_first_diff(a0 ^ b0, a1 ^ b1);
+	L.ll += E < elim ? E : elim;
+	V3_STAT(ext_rounds);
+	if (E < 64u || E >= elim) L.pos = L.lq + L.ll + 1u, L.job = V3_STEP;
+}
+#define V3_BURST_EVERY 8u	 // a warp looks for a burst every so many trips (a power of two): the look itself costs the ordinary walk
+#define V3_BURST_ROUNDS 64u	 // windows per lane and burst at most
+// a burst starts when three in five of the running lanes are in EXT and goes on while three in ten (of those that ran then) are
+V3_FN bool v3_burst_now(u32 ext_lanes, u32 running) { return ext_lanes != 0u && 5u * ext_lanes >= 3u * running; }
+V3_FN bool v3_burst_on(u32 ext_lanes, u32 running) { return ext_lanes != 0u && 10u * ext_lanes >= 3u * running; }
+
 // Classify everything this lane has queued.
 V3_FN void v3_drain_lane(V3Lane &L, const V3Pend &P, u32 *col) {
 	for (u32 k = 0; k < L.npend; k++) v3_classify_entry(P, k, col);

@@ -61,6 +61,8 @@ def parse_args():
                          "genome (exact repeats beyond the direct sort / LCP caps: prefix doubling + phi LCP; experiments only)")
     ap.add_argument("--rows", type=int, default=0, help="subjects per step and rank (default: one full walk batch)")
     ap.add_argument("--model", default="")
+    ap.add_argument("--divergence", default="", help="lo,hi: distance of every genome from the base, uniform (experiments only; "
+                                                     "1e-5,1e-4 = outbreak isolates: anchors of tens of kilobases)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-full", action="store_true", help="skip the whole-matrix (strong scaling) leg")
@@ -76,6 +78,8 @@ def workload_of(args):
         ln = args.length
     if args.model:
         model = args.model
+    if args.divergence:
+        lo, hi = (float(x) for x in args.divergence.split(","))
     return g, ln, lo, hi, seed, model
 
 

@@ -30,6 +30,14 @@ def esa_fixtures():
     return [ESA_FIXTURE_1, ESA_FIXTURE_2]
 
 
+def near_identical_sequences():
+    """Outbreak isolates: three and six SNPs in 60 kbp, anchors of tens of kilobases."""
+    from andi_b200 import synth
+
+    near = synth.base_genome(60000, seed=31)
+    return [synth.ACGT[synth.mutate(near, p, seed=60 + k)].tobytes() for k, p in enumerate((0.0, 5e-5, 1e-4))]
+
+
 def stress_sequences():
     """Small inputs that exercise the corners the reference's tests and SURVEY 7.3 name:
     substitutions only, indels (diagonal changes), join mode ('!'), repeats, identical and
@@ -55,6 +63,7 @@ def stress_sequences():
     for i in range(24):  # ... and a short one in 24 copies: buckets beyond what one thread sorts (index build)
         g[2200 + 1450 * i : 2500 + 1450 * i] = g[100:400]
     out["copies"] = [synth.ACGT[synth.mutate(g, p, seed=40 + k)].tobytes() for k, p in enumerate((0.0, 0.01, 0.03))]
+    out["near"] = near_identical_sequences()
     unrelated = synth.star_phylogeny(1, 20000, [0.0], seed=99)[0]
     out["unrelated"] = [base[0], unrelated]
     out["short"] = [base[0][:50], base[1][:50], base[0][:300], base[1][10:400]]
