@@ -175,3 +175,34 @@ def test_v3_lane_logic_matches_the_oracle(emu, name, chunk, warps, model):
     want = oracle.rows(seqs, model)
     got, stats = emulate_rows(emu, seqs, chunk, warps, model=model)
     assert np.array_equal(got, want), (name, chunk, warps, model, stats)
+
+
+def test_v3_lane_logic_on_random_pools(emu):
+    """Seeded random pools: planted repeats (2 to 20 copies, 50 to 3000 bases), divergences from 0 to 0.3, indels, reverse
+    complements, chunk lengths from 64 bases to one chunk per query, JC and LOGDET -- everything the lane logic has a special
+    path for (cooperative bucket scan, replay beyond the next chunk, EXT bursts), against the oracle."""
+    rng = np.random.default_rng(20261017)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for case in range(24):
+        n = int(rng.integers(3000, 30000))
+        base = synth.base_genome(n, int(rng.integers(1 << 30)))
+        for _ in range(int(rng.integers(0, 4))):
+            ln = int(rng.integers(50, min(3000, n // 4)))
+            src = int(rng.integers(0, n - ln))
+            element = base[src : src + ln].copy()
+            for _ in range(int(rng.integers(1, 20))):
+                at = int(rng.integers(0, n - ln))
+                base[at : at + ln] = element
+        seqs = []
+        for _ in range(int(rng.integers(2, 4))):
+            d = float(rng.choice([0.0, 1e-4, 1e-3, 0.01, 0.03, 0.1, 0.3]))
+            s = synth.ACGT[synth.mutate(base, d, int(rng.integers(1 << 30)))].tobytes()
+            if rng.random() < 0.4:
+                s = synth.with_indels(s, int(rng.integers(1, 8)), int(rng.integers(1, 300)), int(rng.integers(1 << 30)))
+            if rng.random() < 0.15:
+                s = s.translate(comp)[::-1]
+            seqs.append(s)
+        chunk = int(rng.choice([64, 200, 513, 1024, 4096, 1 << 20]))
+        model = str(rng.choice(["JC", "LOGDET"]))
+        got, stats = emulate_rows(emu, seqs, chunk, int(rng.integers(1, 5)), model=model)
+        assert np.array_equal(got, oracle.rows(seqs, model)), (case, n, chunk, model, [len(s) for s in seqs], stats)
