@@ -54,3 +54,21 @@ def test_round2_bench_line():
     # the traffic file belongs to kernel sources by digest
     t = json.loads((ROOT / "profiles" / "walk_traffic.json").read_text())
     assert len(t["kernel_sha"]) == 12 and t["dram_bytes_read"] > 0 and t["pairs_per_launch"] == 3084
+
+
+def test_round2_lines_agree_across_gpu_counts_and_with_the_traffic_capture():
+    """The whole 3085 x 3085 matrix has the same digest at every N (the N > 1 == N = 1 record of the bench), and the
+    headline line quotes the DRAM traffic of the committed capture."""
+    lines = {n: json.loads((ROOT / "profiles" / f"r2_bench_n{n}.json").read_text()) for n in (1, 2, 4, 8)}
+    digests = {d["full_matrix"]["blake2b_of_matrix"] for d in lines.values()}
+    assert len(digests) == 1, digests
+    for n, d in lines.items():
+        assert d["n_gpus"] == n and sum(d["full_matrix"]["rows_per_rank"]) == 3085 and d["full_matrix"]["rows"] == 3085
+        if n > 1:  # weak scaling: every rank does the single-GPU step
+            assert 0.9 < d["value"] / (n * lines[1]["value"]) < 1.1
+    t = json.loads((ROOT / "profiles" / "walk_traffic.json").read_text())
+    assert lines[1]["roofline"]["traffic"] == t["dram_bytes_read"] + t["dram_bytes_write"]
+    # the lines of the pools that are not like the benchmark (DESIGN.md 8.2) are there and are slower than it, not faster
+    for name in ("c4_repeats", "512_repeats", "512_outbreak"):
+        d = json.loads((ROOT / "profiles" / f"r2_bench_{name}.json").read_text())
+        assert d["cub_calls"] == 0 and 0 < d["value"] < lines[1]["value"]
